@@ -1,0 +1,174 @@
+/*
+ * tod.h -- C ABI of libtod.so: the B200 (sm_100a) detector-inference hot path.
+ *
+ * The reference (mohamed22311/Transparent-Object-Detection) is pure Python/PyTorch and has no
+ * FFI layer: the boundary a maintainer binds is the set of plain-C entry
+ * points below, called through ctypes from Python classes that keep the reference's own call
+ * surface (BaseModel / DecodeBox).  Each entry point cites the reference
+ * code it replaces.
+ *
+ * Conventions
+ *   - all pointers named d_* are DEVICE pointers owned by the caller (PyTorch's allocator);
+ *     the library never allocates, frees or synchronises;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, negative = error; tod_last_error() gives a thread-local message;
+ *   - no C++ exceptions cross the ABI; there is no CPU fallback of any kind.
+ *   - activations are NHWC bf16 ("pixels x channels", channel pitch may exceed the logical
+ *     channel count so that producers write straight into concat buffers at a channel offset).
+ */
+#ifndef TOD_H_
+#define TOD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOD_OK 0
+#define TOD_ERR_INVALID (-1)
+#define TOD_ERR_CUDA (-2)
+#define TOD_ERR_UNSUPPORTED (-3)
+
+#define TOD_ACT_NONE 0
+#define TOD_ACT_SILU 1
+
+#define TOD_OUT_BF16 0
+#define TOD_OUT_F32 1
+
+/* library / build identification */
+int tod_version(void);
+const char* tod_last_error(void);
+/* 1 when the current device is compute capability 10.x, else 0 (negative on CUDA error). */
+int tod_device_ok(void);
+
+/*
+ * Fused Conv2d(bias=False) + BatchNorm2d(eval) + SiLU [+ residual] as an NHWC bf16 implicit GEMM on
+ * tcgen05/TMEM fed by TMA.
+ * Replaces: Conv.forward  model/blocks.py:52-54 (with fuse_conv :160-187 folded into w/bias),
+ *           Bottleneck.forward's shortcut add  model/blocks.py:80-82 (residual),
+ *           the bare nn.Conv2d 1x1 + bias of the head  model/head.py:31,42 (act = NONE, out = F32),
+ *           torch.cat / chunk in C2f/SPPF/Neck  model/blocks.py:106-108,139-142, model/neck.py:57-60
+ *           (x/out/residual are channel-offset views of wider buffers),
+ *           nn.Upsample(2,'nearest') feeding a 1x1 conv  model/neck.py:17,57-58 (upadd: the 1x1 conv of
+ *           the low-resolution operand is computed at low resolution and added pre-activation at
+ *           [h>>1][w>>1]).
+ * GEMM view: M = batch*Hout*Wout pixels, N = cout, K = ksize*ksize*cin.
+ * Supported: ksize 1 (stride 1) or 3 (stride 1 or 2, pad 1); cin % 8 == 0; cout % 16 == 0; pitches % 8 == 0;
+ *            stride 2 needs even hin/win.
+ */
+typedef struct tod_conv_desc {
+  const void* d_x;        /* bf16 [batch, hin, win, x_pitch] (already offset to the first input channel) */
+  const void* d_w;        /* bf16 [cout, ksize*ksize*cin_pad], K index = tap*cin_pad + c  (tod_conv_weight_layout) */
+  const float* d_bias;    /* f32 [cout] or NULL */
+  const void* d_residual; /* bf16 [batch, hout, wout, res_pitch] added AFTER activation, or NULL */
+  const float* d_upadd;   /* f32 [batch, hout/2, wout/2, cout] added BEFORE activation at [h>>1][w>>1], or NULL */
+  void* d_out;            /* bf16 or f32 [batch, hout, wout, out_pitch] (already offset to the first output channel) */
+  int32_t batch, hin, win, cin, cout;
+  int32_t ksize, stride;
+  int32_t x_pitch, res_pitch, out_pitch; /* in elements */
+  int32_t act;            /* TOD_ACT_* */
+  int32_t out_dtype;      /* TOD_OUT_* */
+  int32_t block_k;        /* 0 = auto (64/32/16 from cin) */
+  int32_t num_stages;     /* 0 = auto */
+  int32_t reserved[4];
+} tod_conv_desc;
+
+int tod_conv2d_nhwc_bf16(const tod_conv_desc* desc, void* stream);
+
+/* Packed-weight geometry for a conv: *block_k (TMA/UMMA K chunk), *cin_pad (cin rounded up to block_k),
+ * *k_total = ksize*ksize*cin_pad.  Host packers lay weights out as [cout][tap][cin_pad] bf16, zero padded. */
+int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_k_hint,
+                           int32_t* block_k, int32_t* cin_pad, int32_t* k_total);
+
+/*
+ * Stem: Conv2d(3, cout, 3, stride 2, pad 1) + BN + SiLU reading the caller's NCHW fp32 image tensor and
+ * writing NHWC bf16.  Replaces backbone.stem  model/backbone.py:20 (Conv, model/blocks.py:52-54) and the
+ * layout/dtype conversion in front of it.
+ *   d_x   f32 [batch, 3, hin, win]       d_w f32 [cout, 27] (BN folded, K index = c*9 + kh*3 + kw)
+ *   d_out bf16 [batch, hin/2, win/2, out_pitch]
+ */
+int tod_stem_conv_nchw_f32(const float* d_x, const float* d_w, const float* d_bias, void* d_out,
+                           int32_t batch, int32_t hin, int32_t win, int32_t cout, int32_t out_pitch,
+                           void* stream);
+
+/*
+ * SPPF pooling: three chained MaxPool2d(5, 1, 2) evaluated in shared memory.
+ * Replaces SPPF.forward's pooling + torch.cat  model/blocks.py:139-141.
+ * d_buf is the bf16 concat buffer [batch, h, w, pitch] whose channels [0, c) already hold cv1's output;
+ * channels [c,2c), [2c,3c), [3c,4c) receive the 5x5, 9x9, 13x13 max-pools.
+ */
+int tod_sppf_pool_nhwc_bf16(void* d_buf, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t pitch,
+                            void* stream);
+
+/*
+ * Head decode: DFL softmax-expectation, ltrb->xywh about the anchor, x stride, class sigmoid, class max.
+ * Replaces Head.forward eval branch  model/head.py:53-61, DFL.forward  model/blocks.py:154-157,
+ * make_anchors  utils/bbox_utils.py:14-37, dist2bbox :39-58 and DecodeBox.decode_box :66-82.
+ * Inputs: per level l the raw map d_raw[l] = f32 [batch, h_l*w_l, raw_pitch] with channels [0,64) box bins and
+ * [64, 64+nc) class logits (what Head returns in training mode, NHWC).
+ * Outputs (any may be NULL):
+ *   d_head_out f32 [batch, 4+nc, A]   -- Head eval tensor: xywh in input pixels, sigmoid scores
+ *   d_decoded  f32 [batch, A, 4+nc]   -- decode_box: xywh / (W,H,W,H), scores
+ *   d_cand_box f32 [batch, A, 4]      -- NMS-ready corners (cx-w/2, cy-h/2, cx+w/2, cy+h/2 of the normalised xywh,
+ *                                        utils/bbox_utils.py:144-148)
+ *   d_cand_conf f32 [batch, A], d_cand_cls i32 [batch, A] -- class max (lowest class id on ties) and its index
+ */
+typedef struct tod_decode_desc {
+  const float* d_raw[3];
+  int32_t h[3], w[3];
+  float stride[3];
+  int32_t raw_pitch;
+  int32_t batch, nc;
+  int32_t in_h, in_w;  /* network input size (normalisation) */
+  float* d_head_out;
+  float* d_decoded;
+  float* d_cand_box;
+  float* d_cand_conf;
+  int32_t* d_cand_cls;
+  int32_t reserved[4];
+} tod_decode_desc;
+
+int tod_head_decode(const tod_decode_desc* desc, void* stream);
+
+/*
+ * DecodeBox.decode_box applied to an existing Head eval tensor (utils/bbox_utils.py:77-82):
+ * d_head_out f32 [batch, 4+nc, A] -> d_decoded f32 [batch, A, 4+nc] with xywh / (in_w, in_h, in_w, in_h).
+ */
+int tod_decode_box_from_head(const float* d_head_out, float* d_decoded, int32_t batch, int32_t nc, int32_t anchors,
+                             int32_t in_h, int32_t in_w, void* stream);
+
+/*
+ * NMS, step 0 (only for the dense reference-layout tensor): xywh -> corners IN PLACE on
+ * d_prediction f32 [batch, A, 4+nc] (the reference's side effect, utils/bbox_utils.py:144-149) and class max.
+ * Replaces utils/bbox_utils.py:144-153.
+ */
+int tod_nms_prepare_dense(float* d_prediction, int32_t batch, int32_t anchors, int32_t nc,
+                          float* d_cand_box, float* d_cand_conf, int32_t* d_cand_cls, void* stream);
+
+/*
+ * NMS proper: confidence filter (conf >= conf_thres, float32 compare), per-class greedy suppression with
+ * torchvision.ops.nms semantics (IoU in float32, suppressed when (double)IoU > iou_thres), output ordered
+ * class-ascending then score-descending (ties: lower anchor index first).
+ * Replaces DecodeBox.non_max_suppression's per-image / per-class loops  utils/bbox_utils.py:151-175 and
+ * torchvision.ops.nms (:172).
+ *   inputs   d_cand_box f32 [batch, A, 4], d_cand_conf f32 [batch, A], d_cand_cls i32 [batch, A]
+ *   workspace d_work: tod_nms_workspace_bytes(batch, A) bytes
+ *   outputs  d_keep_idx i32 [batch, A] (anchor indices in output order; first d_keep_count[b] valid)
+ *            d_keep_count i32 [batch]
+ *            d_dets f32 [batch, A, 6] rows [x1, y1, x2, y2, conf, cls] in output order, or NULL
+ */
+int64_t tod_nms_workspace_bytes(int32_t batch, int32_t anchors);
+int tod_nms(const float* d_cand_box, const float* d_cand_conf, const int32_t* d_cand_cls,
+            int32_t batch, int32_t anchors, float conf_thres, double iou_thres,
+            void* d_work, int64_t work_bytes,
+            int32_t* d_keep_idx, int32_t* d_keep_count, float* d_dets, void* stream);
+
+/* Debug/verification helper used by tests only: direct (non-tensor-core) evaluation of the same conv
+ * descriptor on CUDA cores, fp32 accumulate.  Never called by the product path. */
+int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOD_H_ */

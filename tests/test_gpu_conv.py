@@ -1,0 +1,109 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv (through the C ABI) against an fp32 torch evaluation of the
+same op on the same bf16-rounded operands, and against the CUDA-core check kernel.
+Tolerance: bf16 output rounding (2^-8 relative) + fp32 accumulation-order noise -> |err| <= 2e-2*|ref| + 2e-2
+for bf16 outputs, 2e-3*|ref| + 2e-3 for f32 outputs (operands are O(1), K up to 4608)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# (name, B, H, W, cin, cout, k, stride, opts)
+CASES = [
+    ("1x1_k64_n64", 1, 16, 16, 64, 64, 1, 1, {}),
+    ("1x1_k256_n128", 2, 20, 20, 256, 128, 1, 1, {}),
+    ("1x1_k96_bk32_views", 2, 12, 16, 96, 64, 1, 1, {"x_pitch": 160, "x_off": 32, "out_pitch": 192, "out_off": 64}),
+    ("1x1_k48_bk16", 1, 8, 8, 48, 32, 1, 1, {}),
+    ("1x1_n512_two_ntiles", 1, 20, 20, 128, 512, 1, 1, {}),
+    ("1x1_n384_two_ntiles", 1, 10, 12, 64, 384, 1, 1, {}),
+    ("1x1_n80_f32_noact", 2, 20, 20, 128, 80, 1, 1, {"f32": True, "act": 0}),
+    ("1x1_small_m", 1, 3, 5, 64, 32, 1, 1, {}),
+    ("1x1_upadd", 2, 8, 12, 64, 64, 1, 1, {"upadd": True}),
+    ("1x1_nobias_f32", 1, 8, 8, 64, 32, 1, 1, {"f32": True, "act": 0, "bias": False}),
+    ("3x3_c64_20x20", 2, 20, 20, 64, 64, 3, 1, {}),
+    ("3x3_c32_res", 2, 16, 24, 32, 32, 3, 1, {"residual": True}),
+    ("3x3_c128_40x40", 1, 40, 40, 128, 128, 3, 1, {}),
+    ("3x3_c16", 1, 12, 16, 16, 16, 3, 1, {}),
+    ("3x3_views_res", 1, 20, 20, 64, 64, 3, 1, {"x_pitch": 256, "x_off": 64, "out_pitch": 256, "out_off": 128,
+                                                  "residual": True}),
+    ("3x3_k4608_n64", 1, 20, 20, 512, 64, 3, 1, {}),
+    ("3x3_n256", 1, 20, 20, 64, 256, 3, 1, {}),
+    ("3x3s2_c64_n128", 2, 32, 32, 64, 128, 3, 2, {}),
+    ("3x3s2_c32_n64_rect", 1, 40, 24, 32, 64, 3, 2, {}),
+    ("3x3s2_c256_n512", 1, 40, 40, 256, 512, 3, 2, {}),
+    ("3x3_stages1", 1, 16, 16, 64, 64, 3, 1, {"stages": 1}),
+    ("3x3_stages2", 1, 16, 16, 64, 64, 3, 1, {"stages": 2}),
+    ("3x3_big_160", 1, 160, 160, 32, 32, 3, 1, {}),
+]
+
+
+def make_case(B, H, W, cin, cout, k, stride, opts, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x_pitch, x_off = opts.get("x_pitch", cin), opts.get("x_off", 0)
+    out_pitch, out_off = opts.get("out_pitch", cout), opts.get("out_off", 0)
+    Ho, Wo = H // stride, W // stride
+    x = torch.randn((B, H, W, x_pitch), generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn((cout, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bias = torch.randn((cout,), generator=g) * 0.5 if opts.get("bias", True) else None
+    dt = torch.float32 if opts.get("f32") else torch.bfloat16
+    out = torch.full((B, Ho, Wo, out_pitch), 7.0, dtype=dt).cuda()
+    res = torch.randn((B, Ho, Wo, out_pitch), generator=g).to(torch.bfloat16).cuda() if opts.get("residual") else None
+    up = torch.randn((B, Ho // 2, Wo // 2, cout), generator=g).cuda() if opts.get("upadd") else None
+    return dict(x=x, x_off=x_off, cin=cin, w=w, bias=bias, out=out, out_off=out_off, stride=stride,
+                act=opts.get("act", 1), res=res, res_off=out_off if res is not None else 0, up=up,
+                stages=opts.get("stages", 0), cout=cout)
+
+
+def run_case(case, simt=False):
+    from tests import gpu_util as U
+    out = torch.full_like(case["out"], 7.0)
+    U.run_conv(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], out, case["out_off"], case["stride"],
+               case["act"], case["res"], case["res_off"], case["up"], 0, case["stages"], simt=simt)
+    want = U.conv_reference(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], case["stride"], case["act"],
+                            case["res"], case["res_off"], case["up"])
+    got = out[..., case["out_off"]:case["out_off"] + case["cout"]].float()
+    return got, want, out
+
+
+@pytest.mark.parametrize("case_def", CASES, ids=[c[0] for c in CASES])
+def test_conv_tcgen05_matches_fp32_reference(case_def):
+    from tests import gpu_util as U
+    name, B, H, W, cin, cout, k, s, opts = case_def
+    case = make_case(B, H, W, cin, cout, k, s, opts)
+    got, want, out = run_case(case)
+    f32 = bool(opts.get("f32"))
+    rep = U.error_report(got, want, name, 2e-3 if f32 else 2e-2, 2e-3 if f32 else 2e-2)
+    assert rep["bad_frac"] == 0 and rep["nan"] == 0, rep
+    # channels outside the output window are untouched (concat-by-offset contract)
+    off, c = case["out_off"], cout
+    if out.shape[-1] > c:
+        mask = torch.ones(out.shape[-1], dtype=torch.bool, device=out.device)
+        mask[off:off + c] = False
+        assert bool((out[..., mask].float() == 7.0).all())
+
+
+@pytest.mark.parametrize("case_def", CASES[:4] + CASES[10:12] + CASES[17:19], ids=lambda c: c[0])
+def test_simt_check_kernel_matches_reference(case_def):
+    from tests import gpu_util as U
+    name, B, H, W, cin, cout, k, s, opts = case_def
+    case = make_case(B, H, W, cin, cout, k, s, opts)
+    got, want, _ = run_case(case, simt=True)
+    f32 = bool(opts.get("f32"))
+    rep = U.error_report(got, want, name, 2e-3 if f32 else 2e-2, 2e-3 if f32 else 2e-2)
+    assert rep["bad_frac"] == 0 and rep["nan"] == 0, rep
+
+
+def test_conv_rejects_bad_arguments():
+    import ctypes as C
+    from transparent_object_detection_b200 import _lib
+    d = _lib.ConvDesc()
+    rc = _lib.lib().tod_conv2d_nhwc_bf16(C.byref(d), None)
+    assert rc == -1 and b"null" in _lib.lib().tod_last_error()
+    x = torch.zeros((1, 8, 8, 24), dtype=torch.bfloat16).cuda()
+    o = torch.zeros((1, 8, 8, 32), dtype=torch.bfloat16).cuda()
+    w = torch.zeros((32, 24), dtype=torch.bfloat16).cuda()
+    d.d_x, d.d_w, d.d_out = x.data_ptr(), w.data_ptr(), o.data_ptr()
+    d.batch, d.hin, d.win, d.cin, d.cout, d.ksize, d.stride = 1, 8, 8, 24, 32, 1, 1
+    d.x_pitch, d.out_pitch = 24, 32
+    assert _lib.lib().tod_conv2d_nhwc_bf16(C.byref(d), None) == -1      # cin % 16 != 0
+    d.cin, d.ksize = 16, 5
+    assert _lib.lib().tod_conv2d_nhwc_bf16(C.byref(d), None) == -1      # unsupported kernel size

@@ -1,0 +1,542 @@
+// NHWC bf16 implicit-GEMM convolution on tcgen05 / TMEM fed by TMA (sm_100a).
+//
+// Replaces reference Conv.forward (model/blocks.py:52-54) with BN folded (fuse_conv, :160-187), the
+// Bottleneck shortcut add (:80-82), the head's bare 1x1 convs (model/head.py:31,42) and -- by reading and
+// writing channel-offset views -- every torch.cat/chunk on the path (see include/tod.h).
+//
+// GEMM view   D[M = pixels, N = cout] = A[M, K] * W[N, K]^T,   K = taps * cin_pad
+//   A tile : 128 output pixels = a TH x TW patch of one image (3x3) or 128 consecutive pixels (1x1, "flat").
+//            For tap (kh, kw) the A operand is the SAME patch shifted by (kh-1, kw-1): one TMA box load per
+//            (tap, channel chunk); out-of-bounds rows/cols are zero-filled by TMA (= the conv's zero padding).
+//            Stride 2 reads four parity sub-lattices of the input through four tensor maps.
+//   W tile : [block_n, block_k] box of the packed [cout, K] weight matrix.
+//   Both land in shared memory in the canonical K-major swizzled layout that tcgen05.mma consumes directly.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+//   warps 2..5 = epilogue (TMEM -> registers -> bias / upsample-add / SiLU / residual -> bf16|f32 -> global).
+#include <cstring>
+#include <mutex>
+
+#include "tod_common.cuh"
+
+namespace tod {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct __align__(64) ConvKernelParams {
+  CUtensorMap tm_a[4];
+  CUtensorMap tm_w;
+  // tiling
+  int hout, wout;          // output spatial dims (flat mode: hout = 1, wout = total pixels)
+  int th, tw;              // patch (th * tw <= 128)
+  int tiles_w, tiles_h;    // tiles per image
+  int cout, block_n, block_k;
+  int num_taps, chunks_per_tap, num_stages;
+  int tap_map[9], tap_dw[9], tap_dh[9];
+  uint32_t stage_a_bytes, stage_b_bytes, tx_bytes;
+  uint32_t idesc;          // tcgen05 instruction descriptor
+  uint32_t desc_hi;        // upper 32 bits of the smem matrix descriptors (SBO, version, swizzle mode)
+  uint32_t tmem_cols;
+  // epilogue
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const float* upadd;
+  void* out;
+  int res_pitch, out_pitch;
+  int up_h, up_w;          // real output dims for the upsample-add (flat mode needs them)
+  int act, out_f32;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t desc_hi) {
+  // bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+  return (static_cast<uint64_t>(desc_hi) << 32) | (1ull << 16) | ((smem_addr >> 4) & 0x3FFFu);
+}
+
+__global__ void __launch_bounds__(kThreads, 2) conv_igemm_tcgen05(const __grid_constant__ ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // 1024-byte aligned tile ring (swizzle atoms are 1024 B)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+
+  // tile coordinates
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int img = blockIdx.x / tiles_per_img;
+  const int trem = blockIdx.x - img * tiles_per_img;
+  const int tile_h = trem / p.tiles_w;
+  const int h0 = tile_h * p.th;
+  const int w0 = (trem - tile_h * p.tiles_w) * p.tw;
+  const int n0 = blockIdx.y * p.block_n;
+  const int num_chunks = p.num_taps * p.chunks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a[0]);
+    tma_prefetch_desc(&p.tm_w);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      for (int i = 0; i < num_chunks; ++i) {
+        const int s = i % p.num_stages;
+        const uint32_t ph = (i / p.num_stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
+        const int tap = i / p.chunks_per_tap;
+        const int cc = i - tap * p.chunks_per_tap;
+        const uint32_t sa = smem_base + s * stage_bytes;
+        tma_load_4d(&p.tm_a[p.tap_map[tap]], &full_bar[s], sa, cc * p.block_k, w0 + p.tap_dw[tap],
+                    h0 + p.tap_dh[tap], img);
+        tma_load_2d(&p.tm_w, &full_bar[s], sa + p.stage_a_bytes, i * p.block_k, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one lane issues)
+    const int ksteps = p.block_k >> 4;  // UMMA_K = 16 for bf16
+    for (int i = 0; i < num_chunks; ++i) {
+      const int s = i % p.num_stages;
+      const uint32_t ph = (i / p.num_stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint64_t da = make_smem_desc(sa, p.desc_hi);
+        const uint64_t db = make_smem_desc(sa + p.stage_a_bytes, p.desc_hi);
+        for (int k = 0; k < ksteps; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, da + 2u * k, db + 2u * k, p.idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                       // smem slot free once these MMAs retire
+        if (i == num_chunks - 1) umma_commit(&accum_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int r = q * 32 + lane;
+    const int pth = r / p.tw;
+    const int h = h0 + pth;
+    const int w = w0 + (r - pth * p.tw);
+    const bool valid = (r < p.th * p.tw) && (h < p.hout) && (w < p.wout);
+    const long long pix = (static_cast<long long>(img) * p.hout + h) * p.wout + w;
+    const float* up_ptr = nullptr;
+    if (p.upadd != nullptr && valid) {
+      long long lp = pix;
+      const int w_ = static_cast<int>(lp % p.up_w);
+      lp /= p.up_w;
+      const int h_ = static_cast<int>(lp % p.up_h);
+      const long long n_ = lp / p.up_h;
+      up_ptr = p.upadd + ((n_ * (p.up_h >> 1) + (h_ >> 1)) * (p.up_w >> 1) + (w_ >> 1)) * p.cout;
+    }
+    const __nv_bfloat16* res_ptr = p.residual ? p.residual + pix * p.res_pitch : nullptr;
+
+    mbar_wait(&accum_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(taddr + c, v);
+      tmem_ld_wait();
+      const int col = n0 + c;
+      if (valid && col < p.cout) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+          }
+        }
+        if (up_ptr) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(up_ptr + col + j));
+            f[j] += u.x; f[j + 1] += u.y; f[j + 2] += u.z; f[j + 3] += u.w;
+          }
+        }
+        if (p.act == TOD_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+        }
+        if (res_ptr) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_ptr + col + j));
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 rf = unpack_bf16x2(rw[t]);
+              f[j + 2 * t] += rf.x;
+              f[j + 2 * t + 1] += rf.y;
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + col;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + col;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint4 ov;
+            ov.x = pack_bf16x2(f[j], f[j + 1]);
+            ov.y = pack_bf16x2(f[j + 2], f[j + 3]);
+            ov.z = pack_bf16x2(f[j + 4], f[j + 5]);
+            ov.w = pack_bf16x2(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = ov;
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core evaluation of the same descriptor (tests only): one thread per (pixel, output channel).
+struct SimtParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* w;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const float* upadd;
+  void* out;
+  int batch, hin, win, cin, cout, hout, wout, ksize, stride, cin_pad;
+  int x_pitch, res_pitch, out_pitch, act, out_f32;
+};
+
+__global__ void conv_simt_check(const SimtParams p) {
+  const long long total = static_cast<long long>(p.batch) * p.hout * p.wout * p.cout;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int co = static_cast<int>(idx % p.cout);
+  const long long pix = idx / p.cout;
+  const int w = static_cast<int>(pix % p.wout);
+  const int h = static_cast<int>((pix / p.wout) % p.hout);
+  const int n = static_cast<int>(pix / (static_cast<long long>(p.wout) * p.hout));
+  const int pad = p.ksize / 2;
+  float acc = 0.f;
+  for (int kh = 0; kh < p.ksize; ++kh)
+    for (int kw = 0; kw < p.ksize; ++kw) {
+      const int ih = h * p.stride + kh - pad, iw = w * p.stride + kw - pad;
+      if (ih < 0 || ih >= p.hin || iw < 0 || iw >= p.win) continue;
+      const __nv_bfloat16* xr = p.x + ((static_cast<long long>(n) * p.hin + ih) * p.win + iw) * p.x_pitch;
+      const __nv_bfloat16* wr = p.w + (static_cast<long long>(co) * p.ksize * p.ksize + kh * p.ksize + kw) * p.cin_pad;
+      for (int c = 0; c < p.cin; ++c) acc = fmaf(__bfloat162float(xr[c]), __bfloat162float(wr[c]), acc);
+    }
+  if (p.bias) acc += p.bias[co];
+  if (p.upadd)
+    acc += p.upadd[((static_cast<long long>(n) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + co];
+  if (p.act == TOD_ACT_SILU) acc = acc / (1.0f + expf(-acc));
+  if (p.residual) acc += __bfloat162float(p.residual[pix * p.res_pitch + co]);
+  if (p.out_f32)
+    reinterpret_cast<float*>(p.out)[pix * p.out_pitch + co] = acc;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.out_pitch + co] = __float2bfloat16_rn(acc);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return TOD_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] "
+              "stride0 %llu base %p",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
+              rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, (unsigned long long)strides_bytes[0], base);
+    return TOD_ERR_CUDA;
+  }
+  return TOD_OK;
+}
+
+static int pick_block_k(int cin, int hint) {
+  if (hint == 16 || hint == 32 || hint == 64) return hint;
+  if (cin % 64 == 0) return 64;
+  if (cin % 32 == 0) return 32;
+  return 16;
+}
+
+// patch shape minimising the number of 128-row tiles for an hout x wout map
+static void pick_patch(int hout, int wout, int* th, int* tw) {
+  long long best = -1;
+  int bth = 1, btw = 1;
+  const int wmax = wout < kTileM ? wout : kTileM;
+  for (int t = 1; t <= wmax; ++t) {
+    int hh = kTileM / t;
+    if (hh > hout) hh = hout;
+    if (hh > 256) hh = 256;
+    const long long tiles = static_cast<long long>(ceil_div(wout, t)) * ceil_div(hout, hh);
+    if (best < 0 || tiles < best || (tiles == best && t > btw)) {
+      best = tiles;
+      bth = hh;
+      btw = t;
+    }
+  }
+  *th = bth;
+  *tw = btw;
+}
+
+static int validate(const tod_conv_desc* d) {
+  TOD_CHECK_ARG(d != nullptr, "conv: null descriptor");
+  TOD_CHECK_ARG(d->d_x && d->d_w && d->d_out, "conv: null x/w/out pointer");
+  TOD_CHECK_ARG(d->batch > 0 && d->hin > 0 && d->win > 0, "conv: bad shape %d x %d x %d", d->batch, d->hin, d->win);
+  TOD_CHECK_ARG((d->ksize == 1 && d->stride == 1) || (d->ksize == 3 && (d->stride == 1 || d->stride == 2)),
+                "conv: unsupported ksize %d stride %d", d->ksize, d->stride);
+  TOD_CHECK_ARG(d->cin >= 16 && d->cin % 16 == 0, "conv: cin %d must be a positive multiple of 16", d->cin);
+  TOD_CHECK_ARG(d->cout >= 16 && d->cout % 16 == 0, "conv: cout %d must be a positive multiple of 16", d->cout);
+  TOD_CHECK_ARG(d->x_pitch >= d->cin && d->x_pitch % 8 == 0, "conv: x_pitch %d", d->x_pitch);
+  TOD_CHECK_ARG(d->out_pitch >= d->cout && d->out_pitch % 8 == 0, "conv: out_pitch %d", d->out_pitch);
+  TOD_CHECK_ARG(!d->d_residual || (d->res_pitch >= d->cout && d->res_pitch % 8 == 0), "conv: res_pitch %d", d->res_pitch);
+  TOD_CHECK_ARG(d->stride == 1 || (d->hin % 2 == 0 && d->win % 2 == 0), "conv: stride 2 needs even input dims");
+  TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d->d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->d_w) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->d_out) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->d_residual) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->d_upadd) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->d_bias) & 15) == 0,
+                "conv: all device pointers must be 16-byte aligned");
+  TOD_CHECK_ARG(d->act == TOD_ACT_NONE || d->act == TOD_ACT_SILU, "conv: bad act %d", d->act);
+  TOD_CHECK_ARG(d->out_dtype == TOD_OUT_BF16 || d->out_dtype == TOD_OUT_F32, "conv: bad out_dtype %d", d->out_dtype);
+  const int hout = d->hin / d->stride, wout = d->win / d->stride;
+  TOD_CHECK_ARG(!d->d_upadd || (hout % 2 == 0 && wout % 2 == 0), "conv: upadd needs even output dims");
+  return TOD_OK;
+}
+
+}  // namespace tod
+
+using namespace tod;
+
+extern "C" int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_k_hint, int32_t* block_k,
+                                      int32_t* cin_pad, int32_t* k_total) {
+  TOD_CHECK_ARG(cin > 0 && (ksize == 1 || ksize == 3), "weight_layout: bad cin %d / ksize %d", cin, ksize);
+  const int bk = pick_block_k(cin, block_k_hint);
+  const int cp = round_up(cin, bk);
+  if (block_k) *block_k = bk;
+  if (cin_pad) *cin_pad = cp;
+  if (k_total) *k_total = ksize * ksize * cp;
+  return TOD_OK;
+}
+
+extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
+  int rc = validate(d);
+  if (rc != TOD_OK) return rc;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_igemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  });
+  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_igemm_tcgen05)")) != TOD_OK) return rc;
+
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  const int hout = d->hin / d->stride, wout = d->win / d->stride;
+  const int bk = pick_block_k(d->cin, d->block_k);
+  const int cin_pad = round_up(d->cin, bk);
+  const int taps = d->ksize * d->ksize;
+  const int k_total = taps * cin_pad;
+  const CUtensorMapSwizzle swz =
+      bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const uint32_t layout_type = bk == 64 ? 2u : (bk == 32 ? 4u : 6u);  // UMMA LayoutType: SW128 / SW64 / SW32
+  const uint32_t row_bytes = bk * 2;
+  const uint32_t sbo = 8 * row_bytes;  // 8-row core-matrix group stride
+
+  // N tiling
+  const int n_tiles = ceil_div(d->cout, 256);
+  const int block_n = round_up(ceil_div(d->cout, n_tiles), 16);
+  p.cout = d->cout;
+  p.block_n = block_n;
+  p.block_k = bk;
+  p.num_taps = taps;
+  p.chunks_per_tap = cin_pad / bk;
+
+  const uint64_t px = static_cast<uint64_t>(d->x_pitch) * 2;  // bytes per input pixel
+  if (d->ksize == 1) {
+    // flat: 128 consecutive pixels per tile
+    const long long mtot = static_cast<long long>(d->batch) * d->hin * d->win;
+    p.hout = 1;
+    p.wout = static_cast<int>(mtot);
+    p.th = 1;
+    p.tw = mtot < kTileM ? static_cast<int>(mtot) : kTileM;
+    p.tiles_h = 1;
+    p.tiles_w = ceil_div(static_cast<int>(mtot), p.tw);
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(mtot), 1, 1};
+    const uint64_t str[3] = {px, px * mtot, px * mtot};
+    const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.tw), 1, 1};
+    if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz)) != TOD_OK) return rc;
+    p.tap_map[0] = 0;
+  } else {
+    p.hout = hout;
+    p.wout = wout;
+    pick_patch(hout, wout, &p.th, &p.tw);
+    p.tiles_h = ceil_div(hout, p.th);
+    p.tiles_w = ceil_div(wout, p.tw);
+    const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th), 1};
+    if (d->stride == 1) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
+                                static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz)) != TOD_OK) return rc;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          p.tap_map[kh * 3 + kw] = 0;
+          p.tap_dh[kh * 3 + kw] = kh - 1;
+          p.tap_dw[kh * 3 + kw] = kw - 1;
+        }
+    } else {
+      // input row 2*oh + kh - 1:  kh=0 -> (oh-1, parity 1), kh=1 -> (oh, 0), kh=2 -> (oh, 1); same for columns
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win / 2),
+                                static_cast<uint64_t>(d->hin / 2), static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {px * 2, px * d->win * 2, px * d->win * d->hin};
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(d->d_x) + (static_cast<uint64_t>(ph) * d->win + pw) * px;
+          if ((rc = encode_map(&p.tm_a[ph * 2 + pw], base, 4, dims, str, box, swz)) != TOD_OK) return rc;
+        }
+      const int par[3] = {1, 0, 1}, off[3] = {-1, 0, 0};
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          p.tap_map[kh * 3 + kw] = par[kh] * 2 + par[kw];
+          p.tap_dh[kh * 3 + kw] = off[kh];
+          p.tap_dw[kh * 3 + kw] = off[kw];
+        }
+    }
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(k_total), static_cast<uint64_t>(d->cout)};
+    const uint64_t str[1] = {static_cast<uint64_t>(k_total) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(block_n)};
+    if ((rc = encode_map(&p.tm_w, d->d_w, 2, dims, str, box, swz)) != TOD_OK) return rc;
+  }
+
+  p.stage_a_bytes = kTileM * row_bytes;
+  p.stage_b_bytes = round_up(block_n * row_bytes, 1024);
+  p.tx_bytes = static_cast<uint32_t>(p.th * p.tw) * row_bytes + block_n * row_bytes;
+  const int num_chunks = taps * p.chunks_per_tap;
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  int stages = d->num_stages;
+  if (stages <= 0) {
+    const uint32_t budget = block_n > 128 ? 200 * 1024 : 100 * 1024;
+    stages = budget / stage_bytes;
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > num_chunks) stages = num_chunks;
+  if (stages < 1) stages = 1;
+  while (stages > 1 && stages * stage_bytes + 1024 > (uint32_t)kSmemLimit) --stages;
+  p.num_stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
+
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) |
+            (static_cast<uint32_t>(kTileM >> 4) << 24);
+  p.desc_hi = (sbo >> 4) | (1u << 14) | (layout_type << 29);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(block_n)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  p.bias = d->d_bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
+  p.upadd = d->d_upadd;
+  p.out = d->d_out;
+  p.res_pitch = d->res_pitch;
+  p.out_pitch = d->out_pitch;
+  p.up_h = hout;
+  p.up_w = wout;
+  p.act = d->act;
+  p.out_f32 = d->out_dtype == TOD_OUT_F32;
+
+  const long long grid_x = static_cast<long long>(d->ksize == 1 ? 1 : d->batch) * p.tiles_h * p.tiles_w;
+  TOD_CHECK_ARG(grid_x > 0 && grid_x < (1ll << 31), "conv: grid too large");
+  dim3 grid(static_cast<unsigned>(grid_x), static_cast<unsigned>(ceil_div(d->cout, block_n)), 1);
+  conv_igemm_tcgen05<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  TOD_CHECK_LAUNCH("conv_igemm_tcgen05 launch");
+  return TOD_OK;
+}
+
+extern "C" int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* d, void* stream) {
+  int rc = validate(d);
+  if (rc != TOD_OK) return rc;
+  SimtParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(d->d_x);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(d->d_w);
+  p.bias = d->d_bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
+  p.upadd = d->d_upadd;
+  p.out = d->d_out;
+  p.batch = d->batch; p.hin = d->hin; p.win = d->win; p.cin = d->cin; p.cout = d->cout;
+  p.hout = d->hin / d->stride; p.wout = d->win / d->stride;
+  p.ksize = d->ksize; p.stride = d->stride;
+  p.cin_pad = round_up(d->cin, pick_block_k(d->cin, d->block_k));
+  p.x_pitch = d->x_pitch; p.res_pitch = d->res_pitch; p.out_pitch = d->out_pitch;
+  p.act = d->act; p.out_f32 = d->out_dtype == TOD_OUT_F32;
+  const long long total = static_cast<long long>(p.batch) * p.hout * p.wout * p.cout;
+  const int threads = 256;
+  conv_simt_check<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0,
+                    static_cast<cudaStream_t>(stream)>>>(p);
+  TOD_CHECK_LAUNCH("conv_simt_check launch");
+  return TOD_OK;
+}

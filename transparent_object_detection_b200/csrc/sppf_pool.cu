@@ -1,0 +1,98 @@
+// SPPF pooling: three chained MaxPool2d(k=5, s=1, p=2) over an NHWC bf16 plane held in shared memory.
+// Replaces SPPF.forward's `y.extend(self.m(y[-1]) for _ in range(3))` + torch.cat (model/blocks.py:139-141):
+// the input already sits in channels [0,c) of the 4c-wide concat buffer (written there by cv1) and the three
+// pooled planes are written to channels [c,2c), [2c,3c), [3c,4c) -- no cat, no intermediate round trip.
+// HBM-bound: reads c*H*W*2 bytes, writes 3x that.  One CTA = one image x one group of CG channels; each 5x5
+// max is done separably (row pass, column pass) with 8-channel (16-byte) vectors; -inf padding == clipped windows.
+#include "tod_common.cuh"
+
+namespace tod {
+
+constexpr int kPoolThreads = 256;
+
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// VEC = number of 8-channel vectors per pixel handled by one CTA (CG = 8 * VEC channels)
+template <int VEC>
+__global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int h, int w, int c,
+                                                                 int pitch) {
+  extern __shared__ uint4 pool_smem[];
+  uint4* b0 = pool_smem;
+  uint4* b1 = pool_smem + static_cast<size_t>(h) * w * VEC;
+  const int groups = c / (8 * VEC);
+  const int n = blockIdx.x / groups;
+  const int c0 = (blockIdx.x - n * groups) * 8 * VEC;
+  const int total = h * w * VEC;
+  __nv_bfloat16* img = buf + static_cast<size_t>(n) * h * w * pitch + c0;
+
+  for (int i = threadIdx.x; i < total; i += kPoolThreads) {
+    const int px = i / VEC, v = i - px * VEC;
+    b0[i] = *reinterpret_cast<const uint4*>(img + static_cast<size_t>(px) * pitch + v * 8);
+  }
+  __syncthreads();
+  for (int stage = 1; stage <= 3; ++stage) {
+    // row pass b0 -> b1
+    for (int i = threadIdx.x; i < total; i += kPoolThreads) {
+      const int px = i / VEC, v = i - px * VEC;
+      const int y = px / w, x = px - y * w;
+      const int xa = x - 2 < 0 ? 0 : x - 2, xb = x + 2 >= w ? w - 1 : x + 2;
+      uint4 m = b0[(y * w + xa) * VEC + v];
+      for (int xx = xa + 1; xx <= xb; ++xx) m = max_bf16x8(m, b0[(y * w + xx) * VEC + v]);
+      b1[i] = m;
+    }
+    __syncthreads();
+    // column pass b1 -> b0 and out to channel slot `stage`
+    for (int i = threadIdx.x; i < total; i += kPoolThreads) {
+      const int px = i / VEC, v = i - px * VEC;
+      const int y = px / w, x = px - y * w;
+      const int ya = y - 2 < 0 ? 0 : y - 2, yb = y + 2 >= h ? h - 1 : y + 2;
+      uint4 m = b1[(ya * w + x) * VEC + v];
+      for (int yy = ya + 1; yy <= yb; ++yy) m = max_bf16x8(m, b1[(yy * w + x) * VEC + v]);
+      b0[i] = m;
+      *reinterpret_cast<uint4*>(img + static_cast<size_t>(px) * pitch + stage * c + v * 8) = m;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace tod
+
+using namespace tod;
+
+extern "C" int tod_sppf_pool_nhwc_bf16(void* d_buf, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t pitch,
+                                       void* stream) {
+  TOD_CHECK_ARG(d_buf != nullptr, "sppf_pool: null buffer");
+  TOD_CHECK_ARG(batch > 0 && h > 0 && w > 0, "sppf_pool: bad shape");
+  TOD_CHECK_ARG(c > 0 && c % 8 == 0 && pitch >= 4 * c && pitch % 8 == 0, "sppf_pool: c %d pitch %d", c, pitch);
+  TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d_buf) & 15) == 0, "sppf_pool: buffer must be 16-byte aligned");
+  static bool attr_done = false;
+  if (!attr_done) {
+    int rc = check_cuda(cudaFuncSetAttribute(sppf_pool_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                        "cudaFuncSetAttribute(sppf_pool<2>)");
+    if (rc != TOD_OK) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(sppf_pool_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                    "cudaFuncSetAttribute(sppf_pool<1>)");
+    if (rc != TOD_OK) return rc;
+    attr_done = true;
+  }
+  const size_t plane16 = static_cast<size_t>(h) * w * 16;  // bytes for one 8-channel vector plane
+  auto st = static_cast<cudaStream_t>(stream);
+  if (c % 16 == 0 && 2 * 2 * plane16 <= 200 * 1024) {
+    sppf_pool_kernel<2><<<batch * (c / 16), kPoolThreads, 2 * 2 * plane16, st>>>(
+        reinterpret_cast<__nv_bfloat16*>(d_buf), h, w, c, pitch);
+  } else {
+    TOD_CHECK_ARG(2 * plane16 <= 200 * 1024, "sppf_pool: %d x %d plane does not fit shared memory", h, w);
+    sppf_pool_kernel<1><<<batch * (c / 8), kPoolThreads, 2 * plane16, st>>>(reinterpret_cast<__nv_bfloat16*>(d_buf), h,
+                                                                            w, c, pitch);
+  }
+  TOD_CHECK_LAUNCH("sppf_pool_kernel launch");
+  return TOD_OK;
+}

@@ -1,0 +1,333 @@
+"""Execution plan for the detector hot path on one B200.
+
+Host-side only: folds BatchNorm into the conv weights (reference fuse_conv, model/blocks.py:160-187),
+packs them to the K-major bf16 layout the tcgen05 kernel consumes, lays the activations out in HBM as
+NHWC bf16 buffers whose concat inputs are pre-allocated (producers write at channel offsets -- no
+torch.cat, no chunk copies), and records the kernel sequence of
+
+    Backbone.forward (model/backbone.py:50-59)  ->  Neck.forward (model/neck.py:55-61, C2f stages per
+    SURVEY F4)  ->  Head.forward (model/head.py:46-61)  ->  decode_box + non_max_suppression
+    (utils/bbox_utils.py:66-82, 119-175)
+
+as a list of C-ABI calls (include/tod.h).  Every arithmetic step runs in libtod.so; PyTorch supplies
+device memory, streams and CUDA-graph capture only.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, DecodeDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_OUT_BF16, TOD_OUT_F32, check
+
+BN_EPS = 1e-5
+
+
+@dataclass
+class View:
+    """A channel window [c_off, c_off + c) of an NHWC buffer (B, h, w, pitch)."""
+    buf: torch.Tensor
+    c_off: int
+    c: int
+
+    @property
+    def h(self) -> int:
+        return self.buf.shape[1]
+
+    @property
+    def w(self) -> int:
+        return self.buf.shape[2]
+
+    @property
+    def pitch(self) -> int:
+        return self.buf.shape[3]
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.c_off * self.buf.element_size()
+
+    def sub(self, off: int, c: int) -> "View":
+        assert 0 <= off and off + c <= self.c
+        return View(self.buf, self.c_off + off, c)
+
+    def tensor(self) -> torch.Tensor:
+        return self.buf[..., self.c_off:self.c_off + self.c]
+
+
+def _t(sd, key) -> torch.Tensor:
+    v = sd[key]
+    if not isinstance(v, torch.Tensor):
+        v = torch.from_numpy(np.asarray(v))
+    return v.detach().to("cpu", torch.float32)
+
+
+def fold_conv_bn(sd, prefix: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """W' = W * g/sqrt(var+eps) per output channel, b' = beta - g*mean/sqrt(var+eps)  (model/blocks.py:179-185)."""
+    w = _t(sd, prefix + ".conv.weight")
+    g, beta = _t(sd, prefix + ".norm.weight"), _t(sd, prefix + ".norm.bias")
+    mean, var = _t(sd, prefix + ".norm.running_mean"), _t(sd, prefix + ".norm.running_var")
+    scale = g / torch.sqrt(var + BN_EPS)
+    return w * scale.view(-1, 1, 1, 1), beta - mean * scale
+
+
+def pack_conv_weight(w: torch.Tensor, block_k_hint: int = 0) -> torch.Tensor:
+    """[cout, cin, k, k] f32 -> [cout, k*k*cin_pad] bf16 with K index = tap*cin_pad + c (tod_conv_weight_layout)."""
+    cout, cin, k, _ = w.shape
+    _, cin_pad, k_total = _lib.weight_layout(cin, k, block_k_hint)
+    p = torch.zeros(cout, k * k, cin_pad, dtype=torch.float32)
+    p[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    return p.reshape(cout, k_total).to(torch.bfloat16).contiguous()
+
+
+class DetectorEngine:
+    """Fixed-shape plan: (batch, 3, in_h, in_w) float32 NCHW in -> raw maps / head tensor / detections."""
+
+    def __init__(self, state_dict, num_classes: int, base_channels: int, base_depth: int, deep_mul: float,
+                 batch: int, in_h: int, in_w: int, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("transparent_object_detection_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.L = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(self.device):
+            ok = self.L.tod_device_ok()
+        if ok != 1:
+            raise RuntimeError("libtod.so targets sm_100a (B200); current device is not compute capability 10.x")
+        if in_h % 32 or in_w % 32:
+            raise ValueError("input height/width must be multiples of 32")
+        self.nc, self.C, self.d, self.deep_mul = num_classes, base_channels, base_depth, deep_mul
+        self.C5 = int(base_channels * 16 * deep_mul)
+        self.batch, self.in_h, self.in_w = batch, in_h, in_w
+        self.ops: List[Tuple[str, str, object]] = []   # (kind, name, payload)
+        self._keep: List[torch.Tensor] = []            # weights / biases kept alive
+        self.conv_flops = 0
+        self.launches_forward = 0
+        self._graph = None
+        self._build(state_dict)
+
+    # ------------------------------------------------------------------ memory
+    def _buf(self, h: int, w: int, c: int, dtype=torch.bfloat16) -> View:
+        t = torch.zeros((self.batch, h, w, c), dtype=dtype, device=self.device)
+        return View(t, 0, c)
+
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.contiguous().to(self.device)
+        self._keep.append(t)
+        return t
+
+    # ------------------------------------------------------------------ op builders
+    def _conv(self, name: str, w: torch.Tensor, b: Optional[torch.Tensor], src: View, dst: View, stride: int = 1,
+              act: int = TOD_ACT_SILU, residual: Optional[View] = None, upadd: Optional[torch.Tensor] = None,
+              out_f32: bool = False) -> None:
+        cout, cin, k, _ = w.shape
+        assert cin == src.c and cout == dst.c, (name, cin, src.c, cout, dst.c)
+        wp = self._dev(pack_conv_weight(w))
+        d = ConvDesc()
+        d.d_x, d.d_w, d.d_out = src.ptr, wp.data_ptr(), dst.ptr
+        d.d_bias = self._dev(b.to(torch.float32)).data_ptr() if b is not None else None
+        d.d_residual = residual.ptr if residual is not None else None
+        d.d_upadd = upadd.data_ptr() if upadd is not None else None
+        d.batch, d.hin, d.win, d.cin, d.cout = self.batch, src.h, src.w, cin, cout
+        d.ksize, d.stride = k, stride
+        d.x_pitch, d.out_pitch = src.pitch, dst.pitch
+        d.res_pitch = residual.pitch if residual is not None else 0
+        d.act, d.out_dtype = act, (TOD_OUT_F32 if out_f32 else TOD_OUT_BF16)
+        assert dst.h == src.h // stride and dst.w == src.w // stride, name
+        self.ops.append(("conv", name, d))
+        self.conv_flops += 2 * self.batch * dst.h * dst.w * cout * cin * k * k
+
+    def _conv_bn(self, sd, prefix: str, src: View, dst: View, stride: int = 1, residual: Optional[View] = None) -> None:
+        w, b = fold_conv_bn(sd, prefix)
+        self._conv(prefix, w, b, src, dst, stride, TOD_ACT_SILU, residual)
+
+    def _c2f(self, sd, prefix: str, src: View, dst: View, n: int, shortcut: bool,
+             up_src: Optional[View] = None) -> None:
+        """reference C2f.forward (model/blocks.py:104-108).  `up_src`: the stage input is
+        cat([upsample2x(up_src), src]) (model/neck.py:57-58): cv1's weight is split column-wise; the up_src part
+        is evaluated at LOW resolution (f32, no bias/act) and added pre-activation at [h>>1][w>>1]."""
+        c = dst.c // 2
+        cat = self._buf(src.h, src.w, (2 + n) * c)
+        w, b = fold_conv_bn(sd, prefix + ".cv1")
+        if up_src is None:
+            self._conv(prefix + ".cv1", w, b, src, cat.sub(0, 2 * c))
+        else:
+            z = torch.zeros((self.batch, up_src.h, up_src.w, 2 * c), dtype=torch.float32, device=self.device)
+            self._keep.append(z)
+            zv = View(z, 0, 2 * c)
+            self._conv(prefix + ".cv1[up]", w[:, :up_src.c].contiguous(), None, up_src, zv, act=TOD_ACT_NONE, out_f32=True)
+            self._conv(prefix + ".cv1", w[:, up_src.c:].contiguous(), b, src, cat.sub(0, 2 * c), upadd=z)
+        tmp = self._buf(src.h, src.w, c)
+        for j in range(n):
+            inp = cat.sub((1 + j) * c, c)
+            self._conv_bn(sd, f"{prefix}.m.{j}.cv1", inp, tmp)
+            self._conv_bn(sd, f"{prefix}.m.{j}.cv2", tmp, cat.sub((2 + j) * c, c), residual=inp if shortcut else None)
+        self._conv_bn(sd, prefix + ".cv2", cat, dst)
+
+    # ------------------------------------------------------------------ the network
+    def _build(self, sd) -> None:
+        C, d, C5, nc, B = self.C, self.d, self.C5, self.nc, self.batch
+        H, W = self.in_h, self.in_w
+        dev = self.device
+        self.x_static = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev)
+        # ---- backbone (model/backbone.py:20-48)
+        w, b = fold_conv_bn(sd, "backbone.stem")
+        stem = self._buf(H // 2, W // 2, C)
+        self.ops.append(("stem", "backbone.stem", (self._dev(w.reshape(C, 27)), self._dev(b), stem)))
+        self.conv_flops += 2 * B * (H // 2) * (W // 2) * C * 27
+        d2 = self._buf(H // 4, W // 4, 2 * C)
+        self._conv_bn(sd, "backbone.dark2.0", stem, d2, 2)
+        d2o = self._buf(H // 4, W // 4, 2 * C)
+        self._c2f(sd, "backbone.dark2.1", d2, d2o, d, True)
+        d3 = self._buf(H // 8, W // 8, 4 * C)
+        self._conv_bn(sd, "backbone.dark3.0", d2o, d3, 2)
+        p3 = self._buf(H // 8, W // 8, 4 * C)
+        self._c2f(sd, "backbone.dark3.1", d3, p3, 2 * d, True)
+        d4 = self._buf(H // 16, W // 16, 8 * C)
+        self._conv_bn(sd, "backbone.dark4.0", p3, d4, 2)
+        p4 = self._buf(H // 16, W // 16, 8 * C)
+        self._c2f(sd, "backbone.dark4.1", d4, p4, 2 * d, True)
+        d5 = self._buf(H // 32, W // 32, C5)
+        self._conv_bn(sd, "backbone.dark5.0", p4, d5, 2)
+        d5o = self._buf(H // 32, W // 32, C5)
+        self._c2f(sd, "backbone.dark5.1", d5, d5o, d, True)
+        # SPPF (model/blocks.py:138-142): cv1 -> slot 0 of the 4*c_ buffer, pools -> slots 1..3, cv2 reads all
+        c_ = C5 // 2
+        sp = self._buf(H // 32, W // 32, 4 * c_)
+        self._conv_bn(sd, "backbone.dark5.2.cv1", d5o, sp.sub(0, c_))
+        self.ops.append(("pool", "backbone.dark5.2.m", (sp, c_)))
+        # neck concat buffers (model/neck.py:57-60): cat6 = [h5(h4) | p5], cat4 = [h3(h2) | h1]
+        cat6 = self._buf(H // 32, W // 32, 8 * C + C5)
+        p5 = cat6.sub(8 * C, C5)
+        self._conv_bn(sd, "backbone.dark5.2.cv2", sp, p5)
+        cat4 = self._buf(H // 16, W // 16, 4 * C + 8 * C)
+        h1 = cat4.sub(4 * C, 8 * C)
+        # ---- neck
+        self._c2f(sd, "neck.h1", p4, h1, d, False, up_src=p5)          # cat([up(p5), p4])
+        h2 = self._buf(H // 8, W // 8, 4 * C)
+        self._c2f(sd, "neck.h2", p3, h2, d, False, up_src=h1)          # cat([up(h1), p3])
+        self._conv_bn(sd, "neck.h3", h2, cat4.sub(0, 4 * C), 2)
+        h4 = self._buf(H // 16, W // 16, 8 * C)
+        self._c2f(sd, "neck.h4", cat4, h4, d, False)                   # cat([h3(h2), h1])
+        self._conv_bn(sd, "neck.h5", h4, cat6.sub(0, 8 * C), 2)
+        h6 = self._buf(H // 32, W // 32, C5)
+        self._c2f(sd, "neck.h6", cat6, h6, d, False)                   # cat([h5(h4), p5])
+        self.features = {"p3": p3, "p4": p4, "p5": p5, "h2": h2, "h4": h4, "h6": h6}
+        # ---- head (model/head.py:19-51)
+        feats = (h2, h4, h6)
+        c1 = max(feats[0].c, nc)
+        c2 = max(feats[0].c // 4, 64)
+        ncp = (nc + 15) // 16 * 16           # class conv output padded to the MMA N granularity
+        self.raw_pitch = 64 + ncp
+        self.raw: List[torch.Tensor] = []
+        for i, f in enumerate(feats):
+            raw = torch.zeros((B, f.h, f.w, self.raw_pitch), dtype=torch.float32, device=dev)
+            self.raw.append(raw)
+            rv = View(raw, 0, self.raw_pitch)
+            tb1, tb2 = self._buf(f.h, f.w, c2), self._buf(f.h, f.w, c2)
+            self._conv_bn(sd, f"head.box.{i}.0", f, tb1)
+            self._conv_bn(sd, f"head.box.{i}.2", tb1, tb2)
+            self._conv(f"head.box.{i}.4", _t(sd, f"head.box.{i}.4.weight"), _t(sd, f"head.box.{i}.4.bias"), tb2,
+                       rv.sub(0, 64), act=TOD_ACT_NONE, out_f32=True)
+            tc1, tc2 = self._buf(f.h, f.w, c1), self._buf(f.h, f.w, c1)
+            self._conv_bn(sd, f"head.cls.{i}.0", f, tc1)
+            self._conv_bn(sd, f"head.cls.{i}.2", tc1, tc2)
+            wc = torch.zeros(ncp, c1, 1, 1)
+            bc = torch.zeros(ncp)
+            wc[:nc] = _t(sd, f"head.cls.{i}.4.weight")
+            bc[:nc] = _t(sd, f"head.cls.{i}.4.bias")
+            self._conv(f"head.cls.{i}.4", wc, bc, tc2, rv.sub(64, ncp), act=TOD_ACT_NONE, out_f32=True)
+        self.level_shapes = [(f.h, f.w) for f in feats]
+        self.anchors = sum(h * w for h, w in self.level_shapes)
+        A = self.anchors
+        # ---- decode + NMS buffers
+        self.head_out = torch.zeros((B, 4 + nc, A), dtype=torch.float32, device=dev)
+        self.decoded = torch.zeros((B, A, 4 + nc), dtype=torch.float32, device=dev)
+        self.cand_box = torch.zeros((B, A, 4), dtype=torch.float32, device=dev)
+        self.cand_conf = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        self.cand_cls = torch.zeros((B, A), dtype=torch.int32, device=dev)
+        self.nms_work = torch.zeros(int(self.L.tod_nms_workspace_bytes(B, A)), dtype=torch.uint8, device=dev)
+        self.keep_idx = torch.zeros((B, A), dtype=torch.int32, device=dev)
+        self.keep_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.dets = torch.zeros((B, A, 6), dtype=torch.float32, device=dev)
+        self.launches_forward = len(self.ops)
+
+    # ------------------------------------------------------------------ execution
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def run_network(self, x: Optional[torch.Tensor] = None) -> None:
+        """Enqueue stem + every conv + SPPF pooling (the raw head maps land in self.raw)."""
+        st = self._stream()
+        L = self.L
+        if x is None:
+            x = self.x_static
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == tuple(self.x_static.shape)
+        for kind, name, payload in self.ops:
+            if kind == "conv":
+                check(L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
+            elif kind == "stem":
+                w, b, out = payload
+                check(L.tod_stem_conv_nchw_f32(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.ptr, self.batch, self.in_h,
+                                               self.in_w, self.C, out.pitch, st), name)
+            elif kind == "pool":
+                buf, c_ = payload
+                check(L.tod_sppf_pool_nhwc_bf16(buf.ptr, self.batch, buf.h, buf.w, c_, buf.pitch, st), name)
+            else:  # pragma: no cover
+                raise AssertionError(kind)
+
+    def run_decode(self, head_out: bool = True, decoded: bool = False, candidates: bool = True) -> None:
+        d = DecodeDesc()
+        for i, (h, w) in enumerate(self.level_shapes):
+            d.d_raw[i] = self.raw[i].data_ptr()
+            d.h[i], d.w[i] = h, w
+            d.stride[i] = float(self.in_h // h)
+        d.raw_pitch, d.batch, d.nc, d.in_h, d.in_w = self.raw_pitch, self.batch, self.nc, self.in_h, self.in_w
+        d.d_head_out = self.head_out.data_ptr() if head_out else None
+        d.d_decoded = self.decoded.data_ptr() if decoded else None
+        if candidates:
+            d.d_cand_box, d.d_cand_conf, d.d_cand_cls = (self.cand_box.data_ptr(), self.cand_conf.data_ptr(),
+                                                         self.cand_cls.data_ptr())
+        check(self.L.tod_head_decode(C.byref(d), self._stream()), "tod_head_decode")
+
+    def run_nms(self, conf_thres: float, nms_thres: float) -> None:
+        check(self.L.tod_nms(self.cand_box.data_ptr(), self.cand_conf.data_ptr(), self.cand_cls.data_ptr(), self.batch,
+                             self.anchors, float(np.float32(conf_thres)), float(nms_thres), self.nms_work.data_ptr(),
+                             self.nms_work.numel(), self.keep_idx.data_ptr(), self.keep_count.data_ptr(),
+                             self.dets.data_ptr(), self._stream()), "tod_nms")
+
+    # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
+    @property
+    def launches_per_pass(self) -> int:
+        return len(self.ops) + 1 + 3
+
+    def capture(self, conf_thres: float, nms_thres: float, head_out: bool = False, decoded: bool = False) -> None:
+        """Capture network + decode + NMS on the static input into one CUDA graph."""
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm-up outside capture (sets function attributes, loads modules)
+                self.run_network()
+                self.run_decode(head_out, decoded, True)
+                self.run_nms(conf_thres, nms_thres)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_network()
+            self.run_decode(head_out, decoded, True)
+            self.run_nms(conf_thres, nms_thres)
+        self._graph = g
+        self._graph_key = (float(conf_thres), float(nms_thres), head_out, decoded)
+
+    def replay(self) -> None:
+        self._graph.replay()
+
+    def raw_maps_nchw(self) -> List[torch.Tensor]:
+        """Training-mode Head output layout (B, 64+nc, h, w) (model/head.py:50-51) as views of the raw maps."""
+        return [r[..., :64 + self.nc].permute(0, 3, 1, 2) for r in self.raw]
+
+    def feature_nchw(self, name: str) -> torch.Tensor:
+        return self.features[name].tensor().permute(0, 3, 1, 2).float()

@@ -1,0 +1,327 @@
+"""Drop-in host surface: the reference's own call signatures over libtod.so.
+
+    BaseModel(num_classes, base_channels, base_depth, deep_mul)      reference model/base.py:7-24
+    DecodeBox(num_classes, input_shape).decode_box / .non_max_suppression / .correct_boxes
+                                                                     reference utils/bbox_utils.py:61-182
+    Detector.detect_image(...)                                       reference utils/callbacks.py:130-179
+                                                                     == dataset/coco/get_map.py:37-96
+
+State-dict compatible with the reference's plain topology: a reference
+`BaseModel.state_dict()` loads with `load_state_dict`.  All arithmetic of forward / decode / NMS runs
+in libtod.so on the GPU; tensors given on the CPU are uploaded (and mutated copies written back where
+the reference mutates its argument) -- nothing is ever computed on the host except the reference's own
+numpy tail (correct_boxes, top-k by confidence), which is numpy in the reference too.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check
+from .engine import DetectorEngine
+
+
+# ----------------------------------------------------------------------------------- parameter tree
+def _conv_entries(prefix: str, c1: int, c2: int, k: int):
+    return [(prefix + ".conv.weight", (c2, c1, k, k), "param"), (prefix + ".norm.weight", (c2,), "param"),
+            (prefix + ".norm.bias", (c2,), "param"), (prefix + ".norm.running_mean", (c2,), "buffer"),
+            (prefix + ".norm.running_var", (c2,), "buffer"), (prefix + ".norm.num_batches_tracked", (), "buffer_i64")]
+
+
+def _c2f_entries(prefix: str, c1: int, c2: int, n: int):
+    c = int(c2 * 0.5)                                               # model/blocks.py:98
+    e = _conv_entries(prefix + ".cv1", c1, 2 * c, 1) + _conv_entries(prefix + ".cv2", (2 + n) * c, c2, 1)
+    for j in range(n):
+        e += _conv_entries(f"{prefix}.m.{j}.cv1", c, c, 3) + _conv_entries(f"{prefix}.m.{j}.cv2", c, c, 3)
+    return e
+
+
+def parameter_table(nc: int, C: int, d: int, deep_mul: float):
+    """(key, shape, kind) in the reference's registration order (backbone.py:20-48, neck.py:19-53 with C2f
+    stages per SURVEY F4, head.py:19-44 with Sequential indices 0/2/4)."""
+    C5 = int(C * 16 * deep_mul)
+    e = _conv_entries("backbone.stem", 3, C, 3)
+    e += _conv_entries("backbone.dark2.0", C, 2 * C, 3) + _c2f_entries("backbone.dark2.1", 2 * C, 2 * C, d)
+    e += _conv_entries("backbone.dark3.0", 2 * C, 4 * C, 3) + _c2f_entries("backbone.dark3.1", 4 * C, 4 * C, 2 * d)
+    e += _conv_entries("backbone.dark4.0", 4 * C, 8 * C, 3) + _c2f_entries("backbone.dark4.1", 8 * C, 8 * C, 2 * d)
+    e += _conv_entries("backbone.dark5.0", 8 * C, C5, 3) + _c2f_entries("backbone.dark5.1", C5, C5, d)
+    e += _conv_entries("backbone.dark5.2.cv1", C5, C5 // 2, 1) + _conv_entries("backbone.dark5.2.cv2", (C5 // 2) * 4, C5, 1)
+    e += _c2f_entries("neck.h1", C5 + 8 * C, 8 * C, d) + _c2f_entries("neck.h2", 12 * C, 4 * C, d)
+    e += _conv_entries("neck.h3", 4 * C, 4 * C, 3) + _c2f_entries("neck.h4", 12 * C, 8 * C, d)
+    e += _conv_entries("neck.h5", 8 * C, 8 * C, 3) + _c2f_entries("neck.h6", C5 + 8 * C, C5, d)
+    filters = (4 * C, 8 * C, C5)
+    c1, c2 = max(filters[0], nc), max(filters[0] // 4, 64)
+    e.append(("head.dfl.conv.weight", (1, 16, 1, 1), "buffer_as_param"))
+    for name, cm, co in (("cls", c1, nc), ("box", c2, 64)):
+        for i, f in enumerate(filters):
+            e += _conv_entries(f"head.{name}.{i}.0", f, cm, 3) + _conv_entries(f"head.{name}.{i}.2", cm, cm, 3)
+            e += [(f"head.{name}.{i}.4.weight", (co, cm, 1, 1), "param"), (f"head.{name}.{i}.4.bias", (co,), "param")]
+    return e
+
+
+class _Node(nn.Module):
+    """Anonymous container so that parameters register under the reference's dotted key paths."""
+
+    def child(self, name: str) -> "_Node":
+        if name not in self._modules:
+            self.add_module(name, _Node())
+        return self._modules[name]
+
+
+class BaseModel(nn.Module):
+    """B200 drop-in for reference `BaseModel` (model/base.py:7-24), plain topology.
+
+    forward(x): x float32 (B, 3, H, W) in [0, 1], H and W multiples of 32.
+      eval  -> float32 (B, 4+nc, A): [cx, cy, w, h] in input pixels + sigmoid class scores (model/head.py:53-61)
+      train -> list of three raw maps (B, 64+nc, h, w)                              (model/head.py:50-51)
+    """
+
+    def __init__(self, num_classes: int, base_channels: int, base_depth: int, deep_mul: float):
+        super().__init__()
+        self.num_classes, self.base_channels, self.base_depth, self.deep_mul = num_classes, base_channels, base_depth, deep_mul
+        for root in ("backbone", "neck", "head"):
+            self.add_module(root, _Node())
+        for key, shape, kind in parameter_table(num_classes, base_channels, base_depth, deep_mul):
+            root, *path, leaf = key.split(".")
+            node = self._modules[root]
+            for p in path:
+                node = node.child(p)
+            if kind == "buffer_i64":
+                node.register_buffer(leaf, torch.zeros((), dtype=torch.int64))
+            elif kind == "buffer":
+                node.register_buffer(leaf, torch.ones(shape) if leaf == "running_var" else torch.zeros(shape))
+            else:
+                if key == "head.dfl.conv.weight":
+                    init = torch.arange(16, dtype=torch.float32).view(shape)           # model/blocks.py:150-152
+                elif leaf == "weight" and len(shape) == 1:
+                    init = torch.ones(shape)
+                elif leaf == "bias":
+                    init = torch.zeros(shape)
+                else:
+                    fan_in = shape[1] * shape[2] * shape[3]
+                    init = torch.randn(shape) * (2.0 / fan_in) ** 0.5
+                node.register_parameter(leaf, nn.Parameter(init, requires_grad=False))
+        self.head.stride = torch.tensor([8.0, 16.0, 32.0])      # the value model/head.py:17 never computes
+        self._engines: Dict[Tuple, DetectorEngine] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._engines.clear())
+
+    # -- engine cache ---------------------------------------------------------------------------
+    def invalidate(self) -> None:
+        """Call after changing weights in place (load_state_dict does it automatically)."""
+        self._engines.clear()
+
+    def engine(self, batch: int, in_h: int, in_w: int, device=None) -> DetectorEngine:
+        device = torch.device("cuda" if device is None else device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = (batch, in_h, in_w, str(device))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = DetectorEngine(self.state_dict(), self.num_classes, self.base_channels, self.base_depth,
+                                 self.deep_mul, batch, in_h, in_w, device)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x: torch.Tensor):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected (B, 3, H, W), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("BaseModel.forward needs a CUDA device: there is no CPU path")
+            x = x.cuda()
+        x = x.contiguous().float()
+        eng = self.engine(x.shape[0], x.shape[2], x.shape[3], x.device)
+        with torch.cuda.device(x.device):
+            eng.run_network(x)
+            if self.training:
+                return [r.contiguous() for r in eng.raw_maps_nchw()]
+            eng.run_decode(head_out=True, decoded=False, candidates=False)
+            return eng.head_out.clone()
+
+    def fuse(self):
+        """reference BaseModel.fuse (model/base.py:26-33): BN is always folded at pack time here."""
+        return self
+
+
+# ----------------------------------------------------------------------------------- DecodeBox
+class DecodeBox:
+    """B200 drop-in for reference `DecodeBox` (utils/bbox_utils.py:61-182)."""
+
+    def __init__(self, num_classes: int, input_shape: Tuple[int, int]):
+        self.num_classes = num_classes
+        self.bbox_attrs = 4 + num_classes
+        self.input_shape = input_shape
+
+    def decode_box(self, inputs) -> torch.Tensor:
+        """utils/bbox_utils.py:66-82.  Accepts the Head eval tensor (B, 4+nc, A) the reference's own head
+        returns -> (B, A, 4+nc) with xywh normalised by (W, H, W, H)."""
+        if isinstance(inputs, (tuple, list)):
+            raise NotImplementedError("decode_box: pass the (B, 4+nc, A) head tensor (the reference head's eval output); "
+                                      "the upstream 5-tuple form is not produced by this model")
+        y = inputs
+        if y.dim() != 3 or y.shape[1] != self.bbox_attrs:
+            raise ValueError(f"decode_box expects (B, {self.bbox_attrs}, A), got {tuple(y.shape)}")
+        was_cpu = not y.is_cuda
+        y = y.cuda().contiguous().float()
+        out = torch.empty((y.shape[0], y.shape[2], y.shape[1]), dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            check(_lib.lib().tod_decode_box_from_head(y.data_ptr(), out.data_ptr(), y.shape[0], self.num_classes,
+                                                      y.shape[2], int(self.input_shape[0]), int(self.input_shape[1]),
+                                                      torch.cuda.current_stream().cuda_stream), "tod_decode_box_from_head")
+        return out.cpu() if was_cpu else out
+
+    @staticmethod
+    def correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image):
+        """utils/bbox_utils.py:84-117 -- host numpy in the reference as well (same dtype flow)."""
+        box_yx = box_xy[..., ::-1]
+        box_hw = box_wh[..., ::-1]
+        input_shape = np.array(input_shape)
+        image_shape = np.array(image_shape)
+        if letterbox_image:
+            new_shape = np.round(image_shape * np.min(input_shape / image_shape))
+            offset = (input_shape - new_shape) / 2.0 / input_shape
+            scale = input_shape / new_shape
+            box_yx = (box_yx - offset) * scale
+            box_hw *= scale
+        box_mins = box_yx - (box_hw / 2.0)
+        box_maxes = box_yx + (box_hw / 2.0)
+        boxes = np.concatenate([box_mins[..., 0:1], box_mins[..., 1:2], box_maxes[..., 0:1], box_maxes[..., 1:2]], axis=-1)
+        boxes *= np.concatenate([image_shape, image_shape], axis=-1)
+        return boxes
+
+    def nms_device(self, prediction: torch.Tensor, num_classes: int, conf_thres: float, nms_thres: float):
+        """Device part: returns (keep_idx (B, A) int32, keep_count (B,) int32, dets (B, A, 6) float32) on the GPU;
+        `prediction` (cuda, contiguous) is rewritten to corner form in place."""
+        B, A, no = prediction.shape
+        dev = prediction.device
+        L = _lib.lib()
+        box = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+        conf = torch.empty((B, A), dtype=torch.float32, device=dev)
+        cls = torch.empty((B, A), dtype=torch.int32, device=dev)
+        work = torch.empty(int(L.tod_nms_workspace_bytes(B, A)), dtype=torch.uint8, device=dev)
+        keep_idx = torch.empty((B, A), dtype=torch.int32, device=dev)
+        keep_count = torch.empty((B,), dtype=torch.int32, device=dev)
+        dets = torch.empty((B, A, 6), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            check(L.tod_nms_prepare_dense(prediction.data_ptr(), B, A, num_classes, box.data_ptr(), conf.data_ptr(),
+                                          cls.data_ptr(), st), "tod_nms_prepare_dense")
+            check(L.tod_nms(box.data_ptr(), conf.data_ptr(), cls.data_ptr(), B, A, float(np.float32(conf_thres)),
+                            float(nms_thres), work.data_ptr(), work.numel(), keep_idx.data_ptr(), keep_count.data_ptr(),
+                            dets.data_ptr(), st), "tod_nms")
+        return keep_idx, keep_count, dets
+
+    def non_max_suppression(self, prediction: torch.Tensor, num_classes: int, input_shape, image_shape,
+                            letterbox_image: bool, conf_thres: float = 0.5, nms_thres: float = 0.4):
+        """utils/bbox_utils.py:119-182: list of None | float32 (n, 6) [y1, x1, y2, x2, conf, cls] in image pixels;
+        rewrites prediction[:, :, :4] to corner form in place like the reference (:144-149)."""
+        if prediction.dim() != 3 or prediction.shape[2] < 4 + num_classes:
+            raise ValueError(f"prediction must be (B, A, >= {4 + num_classes}), got {tuple(prediction.shape)}")
+        if prediction.shape[2] != 4 + num_classes:
+            raise ValueError("prediction's last dimension must be 4 + num_classes")
+        orig = prediction
+        work = prediction
+        if not (work.is_cuda and work.is_contiguous() and work.dtype == torch.float32):
+            work = prediction.detach().to("cuda", torch.float32).contiguous()
+        keep_idx, keep_count, dets = self.nms_device(work, num_classes, conf_thres, nms_thres)
+        if work is not orig:
+            orig.copy_(work.to(orig.device, orig.dtype))      # the in-place side effect
+        counts = keep_count.cpu().numpy()
+        return dets_to_reference_rows(dets, counts, input_shape, image_shape, letterbox_image)
+
+
+def dets_to_reference_rows(dets: torch.Tensor, counts: np.ndarray, input_shape, image_shape, letterbox_image,
+                           empty_is_none: bool = True) -> List[Optional[np.ndarray]]:
+    """Device detections -> the reference's per-image numpy rows (utils/bbox_utils.py:176-180)."""
+    out: List[Optional[np.ndarray]] = [None] * len(counts)
+    mx = int(counts.max()) if len(counts) else 0
+    if mx == 0:
+        return out
+    host = dets[:, :mx].cpu().numpy()
+    for i, n in enumerate(counts):
+        if n == 0:
+            continue
+        o = host[i, :n].copy()
+        box_xy, box_wh = (o[:, 0:2] + o[:, 2:4]) / 2, o[:, 2:4] - o[:, 0:2]
+        o[:, :4] = DecodeBox.correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+        out[i] = o
+    return out
+
+
+# ----------------------------------------------------------------------------------- detector facade
+class Detector:
+    """The in-repo detect pipeline (utils/callbacks.py:130-179 == dataset/coco/get_map.py:37-96) on tensors:
+    net -> decode_box -> non_max_suppression, captured as ONE CUDA graph per (batch, H, W, thresholds)."""
+
+    def __init__(self, model: BaseModel, input_shape: Tuple[int, int], confidence: float = 0.05, nms_iou: float = 0.5,
+                 letterbox_image: bool = True, max_boxes: int = 100):
+        self.model, self.input_shape = model, tuple(input_shape)
+        self.confidence, self.nms_iou, self.letterbox_image, self.max_boxes = confidence, nms_iou, letterbox_image, max_boxes
+        self.bbox_util = DecodeBox(model.num_classes, self.input_shape)
+
+    def _engine(self, batch: int, device) -> DetectorEngine:
+        eng = self.model.engine(batch, self.input_shape[0], self.input_shape[1], device)
+        key = (float(self.confidence), float(self.nms_iou), False, False)
+        if eng._graph is None or eng._graph_key != key:
+            with torch.cuda.device(eng.device):
+                eng.capture(self.confidence, self.nms_iou)
+        return eng
+
+    def detect_device(self, images: torch.Tensor):
+        """images: float32 (B, 3, H, W), host (pinned preferred) or device.  Returns the engine whose
+        keep_count / keep_idx / dets buffers hold the result (no host sync)."""
+        dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        eng = self._engine(images.shape[0], dev)
+        eng.x_static.copy_(images, non_blocking=True)
+        eng.replay()
+        return eng
+
+    def detect(self, images: torch.Tensor, image_shape=None) -> List[Optional[np.ndarray]]:
+        """-> list of None | float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] like non_max_suppression."""
+        eng = self.detect_device(images)
+        counts = eng.keep_count.cpu().numpy()
+        shape = image_shape if image_shape is not None else self.input_shape
+        return dets_to_reference_rows(eng.dets, counts, self.input_shape, shape, self.letterbox_image)
+
+    def detect_image(self, image_id, image, results: list, clsid2catid) -> list:
+        """reference mAP_FOCUS.detect_image (dataset/coco/get_map.py:37-96): `image` is a PIL image or an
+        (H, W, 3) uint8 array; appends COCO-style dicts to `results`."""
+        from PIL import Image
+        if not isinstance(image, Image.Image):
+            image = Image.fromarray(np.asarray(image))
+        image_shape = np.array(np.shape(image)[0:2])
+        image = image if image.mode == "RGB" else image.convert("RGB")                 # utils/utils.py:9-14
+        image_data = _letterbox(image, (self.input_shape[1], self.input_shape[0]), self.letterbox_image)
+        x = np.expand_dims(np.transpose(np.array(image_data, dtype="float32") / 255.0, (2, 0, 1)), 0)
+        out = self.detect(torch.from_numpy(x), image_shape)
+        if out[0] is None:
+            return results
+        top_label = np.array(out[0][:, 5], dtype="int32")
+        top_conf, top_boxes = out[0][:, 4], out[0][:, :4]
+        for i, c in enumerate(top_label):
+            top, left, bottom, right = top_boxes[i]
+            results.append({"image_id": int(image_id), "category_id": clsid2catid[c],
+                            "bbox": [float(left), float(top), float(right - left), float(bottom - top)],
+                            "score": float(top_conf[i])})
+        return results
+
+
+def _letterbox(image, size, letterbox_image):
+    """reference resize_image (utils/utils.py:16-30): PIL BICUBIC, grey (128) padding."""
+    from PIL import Image
+    iw, ih = image.size
+    w, h = size
+    if not letterbox_image:
+        return image.resize((w, h), Image.BICUBIC)
+    scale = min(w / iw, h / ih)
+    nw, nh = int(iw * scale), int(ih * scale)
+    image = image.resize((nw, nh), Image.BICUBIC)
+    new_image = Image.new("RGB", size, (128, 128, 128))
+    new_image.paste(image, ((w - nw) // 2, (h - nh) // 2))
+    return new_image
