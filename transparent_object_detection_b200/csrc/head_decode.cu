@@ -198,12 +198,12 @@ extern "C" int tod_head_decode(const tod_decode_desc* d, void* stream) {
   const size_t smem = (static_cast<size_t>(kDecAnchors) * (d->nc + 1) + kDecAnchors * 4) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    int rc = check_cuda(cudaFuncSetAttribute(head_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+    int rc = check_cuda(cudaFuncSetAttribute(head_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                         "cudaFuncSetAttribute(head_decode)");
     if (rc != TOD_OK) return rc;
     attr_done = true;
   }
-  TOD_CHECK_ARG(smem <= 227 * 1024, "decode: nc %d too large for shared memory", d->nc);
+  TOD_CHECK_ARG(smem <= 200 * 1024, "decode: nc %d too large for shared memory", d->nc);
   dim3 grid(total_tiles, d->batch, 1);
   head_decode_kernel<<<grid, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   TOD_CHECK_LAUNCH("head_decode_kernel launch");
