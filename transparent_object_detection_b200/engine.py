@@ -102,8 +102,9 @@ class DetectorEngine:
         self.C5 = int(base_channels * 16 * deep_mul)
         self.batch, self.in_h, self.in_w = batch, in_h, in_w
         self.ops: List[Tuple[str, str, object]] = []   # (kind, name, payload)
-        self._keep: List[torch.Tensor] = []            # weights / biases kept alive
+        self._keep: List[torch.Tensor] = []            # weights / biases / activation arena kept alive
         self.conv_flops = 0
+        self.conv_meta: Dict[str, dict] = {}          # fp32 weights / views per conv (tools/gpu_netcheck.py)
         self.launches_forward = 0
         self._graph = None
         self._build(state_dict)
@@ -111,6 +112,7 @@ class DetectorEngine:
     # ------------------------------------------------------------------ memory
     def _buf(self, h: int, w: int, c: int, dtype=torch.bfloat16) -> View:
         t = torch.zeros((self.batch, h, w, c), dtype=dtype, device=self.device)
+        self._keep.append(t)   # descriptors hold raw pointers: the arena must outlive them
         return View(t, 0, c)
 
     def _dev(self, t: torch.Tensor) -> torch.Tensor:
@@ -137,6 +139,8 @@ class DetectorEngine:
         d.act, d.out_dtype = act, (TOD_OUT_F32 if out_f32 else TOD_OUT_BF16)
         assert dst.h == src.h // stride and dst.w == src.w // stride, name
         self.ops.append(("conv", name, d))
+        self.conv_meta[name] = dict(w=w, b=b, src=src, dst=dst, stride=stride, act=act, residual=residual, upadd=upadd,
+                                    out_f32=out_f32)
         self.conv_flops += 2 * self.batch * dst.h * dst.w * cout * cin * k * k
 
     def _conv_bn(self, sd, prefix: str, src: View, dst: View, stride: int = 1, residual: Optional[View] = None) -> None:
