@@ -54,7 +54,7 @@ int tod_device_ok(void);
  *           the low-resolution operand is computed at low resolution and added pre-activation at
  *           [h>>1][w>>1]).
  * GEMM view: M = batch*Hout*Wout pixels, N = cout, K = ksize*ksize*cin.
- * Supported: ksize 1 (stride 1) or 3 (stride 1 or 2, pad 1); cin % 8 == 0; cout % 16 == 0; pitches % 8 == 0;
+ * Supported: ksize 1 (stride 1) or 3 (stride 1 or 2, pad 1); cin % 16 == 0; cout % 16 == 0; pitches % 8 == 0;
  *            stride 2 needs even hin/win.
  */
 typedef struct tod_conv_desc {
@@ -85,10 +85,12 @@ int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_k_hint,
  * Stem: Conv2d(3, cout, 3, stride 2, pad 1) + BN + SiLU reading the caller's NCHW fp32 image tensor and
  * writing NHWC bf16.  Replaces backbone.stem  model/backbone.py:20 (Conv, model/blocks.py:52-54) and the
  * layout/dtype conversion in front of it.
- *   d_x   f32 [batch, 3, hin, win]       d_w f32 [cout, 27] (BN folded, K index = c*9 + kh*3 + kw)
- *   d_out bf16 [batch, hin/2, win/2, out_pitch]
+ *   d_x   f32 [batch, 3, hin, win] (device)
+ *   h_w   f32 [cout, 27] HOST pointer (BN folded, K index = c*9 + kh*3 + kw), h_bias f32 [cout] HOST pointer or NULL:
+ *         the 3.5..14 KB of folded weights travel as a kernel parameter (constant bank); cout in {16,32,48,64,96,128}
+ *   d_out bf16 [batch, hin/2, win/2, out_pitch] (device)
  */
-int tod_stem_conv_nchw_f32(const float* d_x, const float* d_w, const float* d_bias, void* d_out,
+int tod_stem_conv_nchw_f32(const float* d_x, const float* h_w, const float* h_bias, void* d_out,
                            int32_t batch, int32_t hin, int32_t win, int32_t cout, int32_t out_pitch,
                            void* stream);
 

@@ -44,17 +44,18 @@ def assert_dets_equal(got, want):
 
 
 # ------------------------------------------------------------------------------------------ stem
-@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 32), (1, 32, 32, 16), (1, 640, 640, 32)])
+@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 32), (1, 32, 32, 16), (1, 640, 640, 32), (1, 64, 64, 96)])
 def test_stem_conv(B, H, W, cout):
     _lib, L = _engine_parts()
     g = torch.Generator().manual_seed(1)
     x = torch.rand((B, 3, H, W), generator=g).cuda()
-    w = (torch.randn((cout, 3, 3, 3), generator=g) * (2.0 / 27) ** 0.5).cuda()
-    b = (torch.randn((cout,), generator=g) * 0.3).cuda()
+    w = torch.randn((cout, 3, 3, 3), generator=g) * (2.0 / 27) ** 0.5          # host: weights are a kernel parameter
+    b = torch.randn((cout,), generator=g) * 0.3
     out = torch.zeros((B, H // 2, W // 2, cout), dtype=torch.bfloat16).cuda()
-    _lib.check(L.tod_stem_conv_nchw_f32(x.data_ptr(), w.reshape(cout, 27).contiguous().data_ptr(), b.data_ptr(),
+    wh = w.reshape(cout, 27).contiguous()
+    _lib.check(L.tod_stem_conv_nchw_f32(x.data_ptr(), wh.data_ptr(), b.data_ptr(),
                                         out.data_ptr(), B, H, W, cout, cout, torch.cuda.current_stream().cuda_stream), "stem")
-    want = F.silu(F.conv2d(x, w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    want = F.silu(F.conv2d(x, w.cuda(), b.cuda(), stride=2, padding=1)).permute(0, 2, 3, 1)
     err = (out.float() - want).abs()
     assert float((err - 1e-2 * want.abs()).max()) <= 1e-2, float(err.max())
 

@@ -29,7 +29,7 @@ def main():
             w, b, out = payload
             check(eng.L.tod_stem_conv_nchw_f32(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.ptr, B, H, W, C_, out.pitch, st), name)
             torch.cuda.synchronize()
-            want = F.silu(F.conv2d(x, w.view(C_, 3, 3, 3), b, stride=2, padding=1)).permute(0, 2, 3, 1)
+            want = F.silu(F.conv2d(x, w.view(C_, 3, 3, 3).cuda(), b.cuda(), stride=2, padding=1)).permute(0, 2, 3, 1)
             got = out.tensor().float()
         elif kind == "pool":
             buf, c_ = payload

@@ -21,8 +21,8 @@
 namespace tod {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
-constexpr int kMaxStages = 8;
+constexpr int kThreads = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 226 * 1024;  // dynamic part; static barriers take <1 KB of the 227 KB opt-in limit
 
 struct __align__(64) ConvKernelParams {
@@ -32,6 +32,7 @@ struct __align__(64) ConvKernelParams {
   int hout, wout;          // output spatial dims (flat mode: hout = 1, wout = total pixels)
   int th, tw;              // patch (th * tw <= 128)
   int tiles_w, tiles_h;    // tiles per image
+  int n_tiles, total_tiles; // N tiles per M tile; M tiles x N tiles (N fastest)
   int cout, block_n, block_k;
   int num_taps, chunks_per_tap, num_stages;
   int tap_map[9], tap_dw[9], tap_dh[9];
@@ -54,11 +55,70 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return (static_cast<uint64_t>(desc_hi) << 32) | (1ull << 16) | ((smem_addr >> 4) & 0x3FFFu);
 }
 
-__global__ void __launch_bounds__(kThreads, 2) conv_igemm_tcgen05(const __grid_constant__ ConvKernelParams p) {
+// One epilogue pass over 16 accumulator columns of one output row.
+__device__ __forceinline__ void epilogue_store16(const ConvKernelParams& p, const uint32_t (&v)[16], int col,
+                                                 long long pix, const float* up_ptr, const __nv_bfloat16* res_ptr) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+      f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+    }
+  }
+  if (up_ptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(up_ptr + col + j));
+      f[j] += u.x; f[j + 1] += u.y; f[j + 2] += u.z; f[j + 3] += u.w;
+    }
+  }
+  if (p.act == TOD_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+  }
+  if (res_ptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_ptr + col + j));
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 rf = unpack_bf16x2(rw[t]);
+        f[j + 2 * t] += rf.x;
+        f[j + 2 * t + 1] += rf.y;
+      }
+    }
+  }
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + col;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + col;
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      uint4 ov;
+      ov.x = pack_bf16x2(f[j], f[j + 1]);
+      ov.y = pack_bf16x2(f[j + 2], f[j + 3]);
+      ov.z = pack_bf16x2(f[j + 4], f[j + 5]);
+      ov.w = pack_bf16x2(f[j + 6], f[j + 7]);
+      *reinterpret_cast<uint4*>(o + j) = ov;
+    }
+  }
+}
+
+// Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring and the two
+// TMEM accumulator stages carry across tiles, so TMA loads of tile i+1/i+2, the MMAs of tile i+1 and the epilogue of
+// tile i overlap.  Epilogue group g (4 warps) owns accumulator stage g = (local tile index) & 1.
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -66,15 +126,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_tcgen05(const __grid_c
   // 1024-byte aligned tile ring (swizzle atoms are 1024 B)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-
-  // tile coordinates
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int img = blockIdx.x / tiles_per_img;
-  const int trem = blockIdx.x - img * tiles_per_img;
-  const int tile_h = trem / p.tiles_w;
-  const int h0 = tile_h * p.th;
-  const int w0 = (trem - tile_h * p.tiles_w) * p.tw;
-  const int n0 = blockIdx.y * p.block_n;
   const int num_chunks = p.num_taps * p.chunks_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -84,7 +136,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_tcgen05(const __grid_c
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);   // one arrival per epilogue warp of the owning group
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -99,121 +154,112 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_tcgen05(const __grid_c
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
-      for (int i = 0; i < num_chunks; ++i) {
-        const int s = i % p.num_stages;
-        const uint32_t ph = (i / p.num_stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
-        const int tap = i / p.chunks_per_tap;
-        const int cc = i - tap * p.chunks_per_tap;
-        const uint32_t sa = smem_base + s * stage_bytes;
-        tma_load_4d(&p.tm_a[p.tap_map[tap]], &full_bar[s], sa, cc * p.block_k, w0 + p.tap_dw[tap],
-                    h0 + p.tap_dh[tap], img);
-        tma_load_2d(&p.tm_w, &full_bar[s], sa + p.stage_a_bytes, i * p.block_k, n0);
+      uint32_t it = 0;  // ring position, continues across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int n0 = (tile - mt * p.n_tiles) * p.block_n;
+        const int img = mt / tiles_per_img;
+        const int trem = mt - img * tiles_per_img;
+        const int tile_h = trem / p.tiles_w;
+        const int h0 = tile_h * p.th;
+        const int w0 = (trem - tile_h * p.tiles_w) * p.tw;
+        for (int i = 0; i < num_chunks; ++i, ++it) {
+          const int s = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
+          const int tap = i / p.chunks_per_tap;
+          const int cc = i - tap * p.chunks_per_tap;
+          const uint32_t sa = smem_base + s * stage_bytes;
+          tma_load_4d(&p.tm_a[p.tap_map[tap]], &full_bar[s], sa, cc * p.block_k, w0 + p.tap_dw[tap],
+                      h0 + p.tap_dh[tap], img);
+          tma_load_2d(&p.tm_w, &full_bar[s], sa + p.stage_a_bytes, i * p.block_k, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one lane issues)
     const int ksteps = p.block_k >> 4;  // UMMA_K = 16 for bf16
-    for (int i = 0; i < num_chunks; ++i) {
-      const int s = i % p.num_stages;
-      const uint32_t ph = (i / p.num_stages) & 1;
-      mbar_wait(&full_bar[s], ph);
+    uint32_t it = 0, lt = 0;            // ring position, local tile index
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((lt >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator stage
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_base + s * stage_bytes;
-        const uint64_t da = make_smem_desc(sa, p.desc_hi);
-        const uint64_t db = make_smem_desc(sa + p.stage_a_bytes, p.desc_hi);
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, da + 2u * k, db + 2u * k, p.idesc, (i | k) != 0 ? 1u : 0u);
+      const uint32_t tmem_d = tmem_base + acc * p.block_n;
+      for (int i = 0; i < num_chunks; ++i, ++it) {
+        const int s = it % p.num_stages;
+        const uint32_t ph = (it / p.num_stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint64_t da = make_smem_desc(sa, p.desc_hi);
+          const uint64_t db = make_smem_desc(sa + p.stage_a_bytes, p.desc_hi);
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                               // smem slot free once these MMAs retire
+          if (i == num_chunks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        umma_commit(&empty_bar[s]);                       // smem slot free once these MMAs retire
-        if (i == num_chunks - 1) umma_commit(&accum_bar);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
+    const int group = (warp - 2) >> 2;   // owns accumulator stage `group`
+    const int q = warp & 3;              // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int r = q * 32 + lane;
     const int pth = r / p.tw;
-    const int h = h0 + pth;
-    const int w = w0 + (r - pth * p.tw);
-    const bool valid = (r < p.th * p.tw) && (h < p.hout) && (w < p.wout);
-    const long long pix = (static_cast<long long>(img) * p.hout + h) * p.wout + w;
-    const float* up_ptr = nullptr;
-    if (p.upadd != nullptr && valid) {
-      long long lp = pix;
-      const int w_ = static_cast<int>(lp % p.up_w);
-      lp /= p.up_w;
-      const int h_ = static_cast<int>(lp % p.up_h);
-      const long long n_ = lp / p.up_h;
-      up_ptr = p.upadd + ((n_ * (p.up_h >> 1) + (h_ >> 1)) * (p.up_w >> 1) + (w_ >> 1)) * p.cout;
-    }
-    const __nv_bfloat16* res_ptr = p.residual ? p.residual + pix * p.res_pitch : nullptr;
+    const int ptw = r - pth * p.tw;
+    const bool in_patch = r < p.th * p.tw;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != static_cast<uint32_t>(group)) continue;
+      const int mt = tile / p.n_tiles;
+      const int n0 = (tile - mt * p.n_tiles) * p.block_n;
+      const int img = mt / tiles_per_img;
+      const int trem = mt - img * tiles_per_img;
+      const int tile_h = trem / p.tiles_w;
+      const int h = tile_h * p.th + pth;
+      const int w = (trem - tile_h * p.tiles_w) * p.tw + ptw;
+      const bool valid = in_patch && (h < p.hout) && (w < p.wout);
+      const long long pix = (static_cast<long long>(img) * p.hout + h) * p.wout + w;
+      const float* up_ptr = nullptr;
+      if (p.upadd != nullptr && valid) {
+        long long lp = pix;
+        const int w_ = static_cast<int>(lp % p.up_w);
+        lp /= p.up_w;
+        const int h_ = static_cast<int>(lp % p.up_h);
+        const long long n_ = lp / p.up_h;
+        up_ptr = p.upadd + ((n_ * (p.up_h >> 1) + (h_ >> 1)) * (p.up_w >> 1) + (w_ >> 1)) * p.cout;
+      }
+      const __nv_bfloat16* res_ptr = p.residual ? p.residual + pix * p.res_pitch : nullptr;
 
-    mbar_wait(&accum_bar, 0);
-    tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c = 0; c < p.block_n; c += 16) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(taddr + c, v);
-      tmem_ld_wait();
-      const int col = n0 + c;
-      if (valid && col < p.cout) {
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-          }
-        }
-        if (up_ptr) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(up_ptr + col + j));
-            f[j] += u.x; f[j + 1] += u.y; f[j + 2] += u.z; f[j + 3] += u.w;
-          }
-        }
-        if (p.act == TOD_ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
-        }
-        if (res_ptr) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_ptr + col + j));
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 rf = unpack_bf16x2(rw[t]);
-              f[j + 2 * t] += rf.x;
-              f[j + 2 * t + 1] += rf.y;
-            }
-          }
-        }
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + col;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + col;
-#pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            uint4 ov;
-            ov.x = pack_bf16x2(f[j], f[j + 1]);
-            ov.y = pack_bf16x2(f[j + 2], f[j + 3]);
-            ov.z = pack_bf16x2(f[j + 4], f[j + 5]);
-            ov.w = pack_bf16x2(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = ov;
-          }
+      mbar_wait(&tmem_full_bar[group], (lt >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * p.block_n;
+      int c = 0;
+      for (; c + 32 <= p.block_n; c += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x32b_x16(taddr + c, v0);
+        tmem_ld_32x32b_x16(taddr + c + 16, v1);
+        tmem_ld_wait();
+        if (valid) {
+          if (n0 + c < p.cout) epilogue_store16(p, v0, n0 + c, pix, up_ptr, res_ptr);
+          if (n0 + c + 16 < p.cout) epilogue_store16(p, v1, n0 + c + 16, pix, up_ptr, res_ptr);
         }
       }
+      if (c < p.block_n) {
+        uint32_t v0[16];
+        tmem_ld_32x32b_x16(taddr + c, v0);
+        tmem_ld_wait();
+        if (valid && n0 + c < p.cout) epilogue_store16(p, v0, n0 + c, pix, up_ptr, res_ptr);
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
     }
   }
 
@@ -314,6 +360,17 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
     return TOD_ERR_CUDA;
   }
   return TOD_OK;
+}
+
+static int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  return sms;
 }
 
 static int pick_block_k(int cin, int hint) {
@@ -478,13 +535,14 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   p.tx_bytes = static_cast<uint32_t>(p.th * p.tw) * row_bytes + block_n * row_bytes;
   const int num_chunks = taps * p.chunks_per_tap;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  // two CTAs per SM when both fit (TMEM: 2 CTAs x 2 stages x block_n columns <= 512); else one CTA with a deep ring
+  const int ctas_per_sm = block_n <= 128 ? 2 : 1;
   int stages = d->num_stages;
   if (stages <= 0) {
-    const uint32_t budget = block_n > 128 ? 200 * 1024 : 100 * 1024;
+    const uint32_t budget = ctas_per_sm == 2 ? 108 * 1024 : 220 * 1024;
     stages = budget / stage_bytes;
   }
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > num_chunks) stages = num_chunks;
   if (stages < 1) stages = 1;
   while (stages > 1 && stages * stage_bytes + 1024 > (uint32_t)kSmemLimit) --stages;
   p.num_stages = stages;
@@ -495,7 +553,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
             (static_cast<uint32_t>(kTileM >> 4) << 24);
   p.desc_hi = (sbo >> 4) | (1u << 14) | (layout_type << 29);
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(block_n)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(2 * block_n)) cols <<= 1;   // two accumulator stages
   p.tmem_cols = cols;
 
   p.bias = d->d_bias;
@@ -509,9 +567,12 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   p.act = d->act;
   p.out_f32 = d->out_dtype == TOD_OUT_F32;
 
-  const long long grid_x = static_cast<long long>(d->ksize == 1 ? 1 : d->batch) * p.tiles_h * p.tiles_w;
-  TOD_CHECK_ARG(grid_x > 0 && grid_x < (1ll << 31), "conv: grid too large");
-  dim3 grid(static_cast<unsigned>(grid_x), static_cast<unsigned>(ceil_div(d->cout, block_n)), 1);
+  const long long m_tiles = static_cast<long long>(d->ksize == 1 ? 1 : d->batch) * p.tiles_h * p.tiles_w;
+  p.n_tiles = ceil_div(d->cout, block_n);
+  TOD_CHECK_ARG(m_tiles > 0 && m_tiles * p.n_tiles < (1ll << 31), "conv: too many tiles");
+  p.total_tiles = static_cast<int>(m_tiles * p.n_tiles);
+  const int slots = num_sms() * ctas_per_sm;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
   conv_igemm_tcgen05<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   TOD_CHECK_LAUNCH("conv_igemm_tcgen05 launch");
   return TOD_OK;

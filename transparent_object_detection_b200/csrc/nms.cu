@@ -20,7 +20,7 @@ namespace tod {
 
 constexpr int kSortThreads = 1024;
 constexpr int kSortSmemKeys = 16384;  // 128 KB of 64-bit keys
-constexpr int kSegWarps = 4;
+constexpr int kSegWarps = 8;
 constexpr int kSegCtasPerImage = 32;
 constexpr int kIdxBits = 20, kScoreBits = 32;  // key = cls[12] | ~score[32] | idx[20]
 constexpr unsigned long long kIdxMask = (1ull << kIdxBits) - 1;
@@ -187,80 +187,103 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
   return ovr > thr;
 }
 
+// One CTA per (image, class) segment.  Greedy NMS processes boxes in score order; a box's fate is known once it has
+// been compared with every EARLIER KEPT box.  Each round, warp 0 gathers the next <= 32 boxes that are still alive
+// (dead ones are skipped for good), resolves them among themselves (per-lane 32-bit IoU masks + a shuffle scan) and
+// publishes the kept ones; then the whole CTA sweeps the not-yet-visited tail of the segment against those kept boxes.
+// Work is O(kept x segment) instead of O(segment^2); the result is exactly the sequential greedy one.
 __global__ void __launch_bounds__(kSegWarps * 32) nms_segment_kernel(const float4* __restrict__ cand_box, int anchors,
                                                                      float iou_thr, NmsWork wk) {
+  __shared__ float4 s_kept[32];
+  __shared__ int s_tilepos[32];
+  __shared__ int s_pos, s_cnt, s_nk;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int wslot = blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
   const int nseg = wk.n_seg[b];
   const float4* boxes = cand_box + static_cast<size_t>(b) * anchors;
   const int* order = wk.order + static_cast<size_t>(b) * anchors;
-  unsigned char* flags = wk.flags + static_cast<size_t>(b) * anchors;
+  unsigned char* flags_img = wk.flags + static_cast<size_t>(b) * anchors;
   const unsigned full = 0xffffffffu;
 
-  for (int seg = wslot; seg < nseg; seg += kSegCtasPerImage * kSegWarps) {
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
     const int s0 = wk.seg_start[b * static_cast<size_t>(anchors) + seg];
     const int len = wk.seg_len[b * static_cast<size_t>(anchors) + seg];
-    for (int t0 = 0; t0 < len; t0 += 32) {
-      const int i = t0 + lane;
-      const bool has = i < len;
-      float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool alive = false;
-      if (has) {
-        bi = boxes[order[s0 + i]];
-        alive = (flags[s0 + i] & 1) == 0;
-      }
-      const float area_i = (bi.z - bi.x) * (bi.w - bi.y);
-      // bitmask of later in-tile boxes this box would suppress
-      unsigned mask = 0;
-#pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-        float4 bj;
-        bj.x = __shfl_sync(full, bi.x, j);
-        bj.y = __shfl_sync(full, bi.y, j);
-        bj.z = __shfl_sync(full, bi.z, j);
-        bj.w = __shfl_sync(full, bi.w, j);
-        const float area_j = __shfl_sync(full, area_i, j);
-        if (j > lane && iou_gt(bi, area_i, bj, area_j, iou_thr)) mask |= 1u << j;
-      }
-      // greedy scan over the tile in score order
-      unsigned alive_bits = __ballot_sync(full, alive);
-      const int tile_n = min(32, len - t0);
-      for (int j = 0; j < tile_n; ++j) {
-        const unsigned mj = __shfl_sync(full, mask, j);
-        if ((alive_bits >> j) & 1u) alive_bits &= ~mj;
-      }
-      const bool kept = has && ((alive_bits >> lane) & 1u);
-      if (kept) flags[s0 + i] |= 2;
-      // kept boxes of this tile suppress the remainder of the segment
-      if (alive_bits != 0) {
-        for (int k0 = t0 + 32; k0 < len; k0 += 32) {
-          const int k = k0 + lane;
-          const bool hk = k < len;
-          float4 bk = make_float4(0.f, 0.f, 0.f, 0.f);
-          bool dead = true;
-          if (hk) {
-            dead = (flags[s0 + k] & 1) != 0;
-            if (!dead) bk = boxes[order[s0 + k]];
+    unsigned char* flags = flags_img + s0;   // bit0 = suppressed, bit1 = kept
+    const int* ord = order + s0;
+    if (threadIdx.x == 0) s_pos = 0;
+    __syncthreads();
+    while (true) {
+      if (warp == 0) {
+        // ---- gather the next <= 32 alive boxes in score order
+        int pos = s_pos, cnt = 0;
+        while (cnt < 32 && pos < len) {
+          const int pp = pos + lane;
+          const bool al = pp < len && (flags[pp] & 1) == 0;
+          const unsigned bal = __ballot_sync(full, al);
+          const int avail = __popc(bal);
+          const int take = min(avail, 32 - cnt);
+          const int rank = __popc(bal & ((1u << lane) - 1u));
+          if (al && rank < take) s_tilepos[cnt + rank] = pp;
+          if (take < avail) {
+            const unsigned last = __ballot_sync(full, al && rank == take - 1);
+            pos += __ffs(last);          // one past the last box taken
+          } else {
+            pos += 32;
           }
-          if (__ballot_sync(full, !dead) == 0) continue;
-          const float area_k = (bk.z - bk.x) * (bk.w - bk.y);
-          unsigned rem = alive_bits;
-          while (rem) {
-            const int j = __ffs(rem) - 1;
-            rem &= rem - 1;
-            float4 bj;
-            bj.x = __shfl_sync(full, bi.x, j);
-            bj.y = __shfl_sync(full, bi.y, j);
-            bj.z = __shfl_sync(full, bi.z, j);
-            bj.w = __shfl_sync(full, bi.w, j);
-            const float area_j = __shfl_sync(full, area_i, j);
-            if (!dead && iou_gt(bj, area_j, bk, area_k, iou_thr)) dead = true;
-          }
-          if (hk && dead) flags[s0 + k] |= 1;
+          cnt += take;
+        }
+        __syncwarp();
+        // ---- resolve the tile: lane i owns the i-th gathered box (all are alive on entry)
+        const bool has = lane < cnt;
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        int my = 0;
+        if (has) {
+          my = s_tilepos[lane];
+          bi = boxes[ord[my]];
+        }
+        const float area_i = (bi.z - bi.x) * (bi.w - bi.y);
+        unsigned mask = 0;   // later in-tile boxes this box suppresses
+        for (int j = 1; j < cnt; ++j) {
+          float4 bj;
+          bj.x = __shfl_sync(full, bi.x, j);
+          bj.y = __shfl_sync(full, bi.y, j);
+          bj.z = __shfl_sync(full, bi.z, j);
+          bj.w = __shfl_sync(full, bi.w, j);
+          const float area_j = __shfl_sync(full, area_i, j);
+          if (j > lane && iou_gt(bi, area_i, bj, area_j, iou_thr)) mask |= 1u << j;
+        }
+        unsigned alive_bits = cnt >= 32 ? full : ((1u << cnt) - 1u);
+        for (int j = 0; j < cnt; ++j) {
+          const unsigned mj = __shfl_sync(full, mask, j);
+          if ((alive_bits >> j) & 1u) alive_bits &= ~mj;
+        }
+        const bool kept = has && ((alive_bits >> lane) & 1u);
+        if (has) flags[my] |= kept ? 2 : 1;
+        if (kept) s_kept[__popc(alive_bits & ((1u << lane) - 1u))] = bi;
+        if (lane == 0) {
+          s_pos = pos < len ? pos : len;
+          s_cnt = cnt;
+          s_nk = __popc(alive_bits);
         }
       }
-      __syncwarp();
+      __syncthreads();
+      const int cnt = s_cnt, nk = s_nk, pos = s_pos;
+      if (cnt == 0) break;
+      // ---- kept boxes of this round suppress the unvisited tail
+      for (int k = pos + threadIdx.x; k < len; k += kSegWarps * 32) {
+        if (flags[k] & 1) continue;
+        const float4 bk = boxes[ord[k]];
+        const float area_k = (bk.z - bk.x) * (bk.w - bk.y);
+        for (int j = 0; j < nk; ++j) {
+          const float4 bj = s_kept[j];
+          if (iou_gt(bj, (bj.z - bj.x) * (bj.w - bj.y), bk, area_k, iou_thr)) {
+            flags[k] |= 1;
+            break;
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 }

@@ -1,31 +1,33 @@
 // Stem: Conv2d(3, cout, 3, s2, p1) + folded BN + SiLU, NCHW fp32 in -> NHWC bf16 out.
 // Replaces backbone.stem (model/backbone.py:20; Conv.forward model/blocks.py:52-54).
 // K = 27 is too thin for a tensor-core tile and the layer is HBM-bound (reads the fp32 image once, writes
-// cout bf16 per output pixel), so it runs on CUDA cores: one thread per output pixel, weights broadcast
-// from shared memory, 16-byte vector stores.
+// cout bf16 per output pixel), so it runs on CUDA cores: one thread per output pixel, all cout channels.
+// The folded weights travel as a __grid_constant__ kernel parameter: with fully unrolled loops every FFMA takes
+// its weight straight from the constant bank (no shared/global weight loads at all); 16-byte vector stores.
+#include <cstring>
+
 #include "tod_common.cuh"
 
 namespace tod {
 
 constexpr int kStemThreads = 128;
-constexpr int kStemMaxCout = 128;
 
+template <int COUT>
+struct StemWeights {
+  float w[COUT * 27];   // [cout][c*9 + kh*3 + kw]
+  float b[COUT];
+};
+
+template <int COUT>
 __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __restrict__ x,
-                                                                 const float* __restrict__ w,
-                                                                 const float* __restrict__ bias,
-                                                                 __nv_bfloat16* __restrict__ out, int batch, int hin,
-                                                                 int win, int cout, int out_pitch) {
-  __shared__ float sw[kStemMaxCout * 27];
-  __shared__ float sb[kStemMaxCout];
-  for (int i = threadIdx.x; i < cout * 27; i += kStemThreads) sw[i] = w[i];
-  for (int i = threadIdx.x; i < cout; i += kStemThreads) sb[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-
+                                                                 __nv_bfloat16* __restrict__ out, int hin, int win,
+                                                                 int out_pitch,
+                                                                 const __grid_constant__ StemWeights<COUT> wt) {
   const int hout = hin >> 1, wout = win >> 1;
-  const int ow = blockIdx.x * kStemThreads + threadIdx.x;
-  const int oh = blockIdx.y;
-  const int n = blockIdx.z;
-  if (ow >= wout) return;
+  const int pix = blockIdx.x * kStemThreads + threadIdx.x;
+  const int n = blockIdx.y;
+  if (pix >= hout * wout) return;
+  const int oh = pix / wout, ow = pix - oh * wout;
 
   float v[27];
   const size_t plane = static_cast<size_t>(hin) * win;
@@ -43,15 +45,15 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
       }
     }
 
-  __nv_bfloat16* o = out + ((static_cast<size_t>(n) * hout + oh) * wout + ow) * out_pitch;
-  for (int co = 0; co < cout; co += 8) {
+  __nv_bfloat16* o = out + (static_cast<size_t>(n) * hout * wout + pix) * out_pitch;
+#pragma unroll
+  for (int co = 0; co < COUT; co += 8) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float a = sb[co + j];
-      const float* wr = sw + (co + j) * 27;
+      float a = wt.b[co + j];
 #pragma unroll
-      for (int k = 0; k < 27; ++k) a = fmaf(v[k], wr[k], a);
+      for (int k = 0; k < 27; ++k) a = fmaf(v[k], wt.w[(co + j) * 27 + k], a);
       acc[j] = silu_f(a);
     }
     uint4 ov;
@@ -63,24 +65,41 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv_kernel(const float* __
   }
 }
 
+template <int COUT>
+static int launch_stem(const float* d_x, const float* h_w, const float* h_bias, void* d_out, int batch, int hin, int win,
+                       int out_pitch, cudaStream_t st) {
+  StemWeights<COUT> wt;
+  memcpy(wt.w, h_w, sizeof(wt.w));
+  if (h_bias) memcpy(wt.b, h_bias, sizeof(wt.b)); else memset(wt.b, 0, sizeof(wt.b));
+  dim3 grid(ceil_div((hin / 2) * (win / 2), kStemThreads), batch, 1);
+  stem_conv_kernel<COUT><<<grid, kStemThreads, 0, st>>>(d_x, reinterpret_cast<__nv_bfloat16*>(d_out), hin, win, out_pitch, wt);
+  TOD_CHECK_LAUNCH("stem_conv_kernel launch");
+  return TOD_OK;
+}
+
 }  // namespace tod
 
 using namespace tod;
 
-extern "C" int tod_stem_conv_nchw_f32(const float* d_x, const float* d_w, const float* d_bias, void* d_out,
+extern "C" int tod_stem_conv_nchw_f32(const float* d_x, const float* h_w, const float* h_bias, void* d_out,
                                       int32_t batch, int32_t hin, int32_t win, int32_t cout, int32_t out_pitch,
                                       void* stream) {
-  TOD_CHECK_ARG(d_x && d_w && d_out, "stem: null pointer");
+  TOD_CHECK_ARG(d_x && h_w && d_out, "stem: null pointer");
   TOD_CHECK_ARG(batch > 0 && hin > 0 && win > 0 && hin % 2 == 0 && win % 2 == 0, "stem: bad shape %d x %d x %d", batch,
                 hin, win);
-  TOD_CHECK_ARG(cout > 0 && cout % 8 == 0 && cout <= kStemMaxCout, "stem: cout %d must be a multiple of 8, <= %d", cout,
-                kStemMaxCout);
   TOD_CHECK_ARG(out_pitch >= cout && out_pitch % 8 == 0, "stem: out_pitch %d", out_pitch);
   TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "stem: output must be 16-byte aligned");
-  TOD_CHECK_ARG(hin / 2 <= 65535 && batch <= 65535, "stem: grid too large");
-  dim3 grid(ceil_div(win / 2, kStemThreads), hin / 2, batch);
-  stem_conv_kernel<<<grid, kStemThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_x, d_w, d_bias, reinterpret_cast<__nv_bfloat16*>(d_out), batch, hin, win, cout, out_pitch);
-  TOD_CHECK_LAUNCH("stem_conv_kernel launch");
-  return TOD_OK;
+  TOD_CHECK_ARG(batch <= 65535, "stem: batch too large");
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (cout) {
+    case 16: return launch_stem<16>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 32: return launch_stem<32>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 48: return launch_stem<48>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 64: return launch_stem<64>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 96: return launch_stem<96>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 128: return launch_stem<128>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    default:
+      set_error("stem: unsupported cout %d (supported: 16, 32, 48, 64, 96, 128)", cout);
+      return TOD_ERR_UNSUPPORTED;
+  }
 }

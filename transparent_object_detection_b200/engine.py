@@ -179,7 +179,9 @@ class DetectorEngine:
         # ---- backbone (model/backbone.py:20-48)
         w, b = fold_conv_bn(sd, "backbone.stem")
         stem = self._buf(H // 2, W // 2, C)
-        self.ops.append(("stem", "backbone.stem", (self._dev(w.reshape(C, 27)), self._dev(b), stem)))
+        wh, bh = w.reshape(C, 27).contiguous().float(), b.contiguous().float()      # HOST tensors (kernel parameter)
+        self._keep += [wh, bh]
+        self.ops.append(("stem", "backbone.stem", (wh, bh, stem)))
         self.conv_flops += 2 * B * (H // 2) * (W // 2) * C * 27
         d2 = self._buf(H // 4, W // 4, 2 * C)
         self._conv_bn(sd, "backbone.dark2.0", stem, d2, 2)
