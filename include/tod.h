@@ -170,6 +170,10 @@ int tod_nms(const float* d_cand_box, const float* d_cand_conf, const int32_t* d_
  * descriptor on CUDA cores, fp32 accumulate.  Never called by the product path. */
 int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* desc, void* stream);
 
+/* Debug/profiling helper used by tools only: when d_buf is non-NULL the halo conv kernel records per-CTA wait-cycle
+ * counters (16 x uint64 per CTA, see conv_halo_tcgen05.cu) into it; NULL switches recording off. */
+int tod_debug_set_conv_profile(void* d_buf);
+
 #ifdef __cplusplus
 }
 #endif

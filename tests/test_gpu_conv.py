@@ -33,7 +33,20 @@ CASES = [
     ("3x3_stages1", 1, 16, 16, 64, 64, 3, 1, {"stages": 1}),
     ("3x3_stages2", 1, 16, 16, 64, 64, 3, 1, {"stages": 2}),
     ("3x3_big_160", 1, 160, 160, 32, 32, 3, 1, {}),
+    ("3x3_40x40_partial_rows", 2, 40, 40, 64, 64, 3, 1, {"residual": True}),
+    ("3x3_tiny_6x6", 3, 6, 6, 32, 48, 3, 1, {}),
+    ("3x3_c256_n128_ring", 1, 24, 24, 256, 128, 3, 1, {}),
+    ("3x3_c128_n128_m1", 2, 16, 16, 128, 128, 3, 1, {"m": 1}),
+    ("3x3_c64_ring", 2, 32, 16, 64, 64, 3, 1, {"no_station": 1}),
+    ("3x3s2_c128_n128", 2, 48, 32, 128, 128, 3, 2, {}),
+    ("3x3s2_c16_n32_odd_tiles", 1, 20, 28, 16, 32, 3, 2, {}),
+    ("1x1_k512_n256_ring", 1, 40, 40, 512, 256, 1, 1, {}),
+    ("1x1_k768_n512", 1, 20, 20, 768, 512, 1, 1, {}),
+    ("1x1_n144_f32", 1, 16, 16, 64, 144, 1, 1, {"f32": True, "act": 0}),
+    ("1x1_m_not_mult_128", 3, 7, 9, 32, 32, 1, 1, {}),
+    ("1x1_res_views", 2, 16, 16, 64, 64, 1, 1, {"residual": True, "out_pitch": 128, "out_off": 64}),
 ]
+VARIANTS = {"pertap": 1, "halo": 2}
 
 
 def make_case(B, H, W, cin, cout, k, stride, opts, seed=0):
@@ -50,26 +63,28 @@ def make_case(B, H, W, cin, cout, k, stride, opts, seed=0):
     up = torch.randn((B, Ho // 2, Wo // 2, cout), generator=g).cuda() if opts.get("upadd") else None
     return dict(x=x, x_off=x_off, cin=cin, w=w, bias=bias, out=out, out_off=out_off, stride=stride,
                 act=opts.get("act", 1), res=res, res_off=out_off if res is not None else 0, up=up,
-                stages=opts.get("stages", 0), cout=cout)
+                stages=opts.get("stages", 0), cout=cout, m=opts.get("m", 0), no_station=opts.get("no_station", 0))
 
 
-def run_case(case, simt=False):
+def run_case(case, simt=False, variant=0):
     from tests import gpu_util as U
     out = torch.full_like(case["out"], 7.0)
     U.run_conv(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], out, case["out_off"], case["stride"],
-               case["act"], case["res"], case["res_off"], case["up"], 0, case["stages"], simt=simt)
+               case["act"], case["res"], case["res_off"], case["up"], 0, case["stages"], simt=simt, variant=variant,
+               m=case["m"], no_station=case["no_station"])
     want = U.conv_reference(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], case["stride"], case["act"],
                             case["res"], case["res_off"], case["up"])
     got = out[..., case["out_off"]:case["out_off"] + case["cout"]].float()
     return got, want, out
 
 
+@pytest.mark.parametrize("variant", list(VARIANTS), ids=list(VARIANTS))
 @pytest.mark.parametrize("case_def", CASES, ids=[c[0] for c in CASES])
-def test_conv_tcgen05_matches_fp32_reference(case_def):
+def test_conv_tcgen05_matches_fp32_reference(case_def, variant):
     from tests import gpu_util as U
     name, B, H, W, cin, cout, k, s, opts = case_def
     case = make_case(B, H, W, cin, cout, k, s, opts)
-    got, want, out = run_case(case)
+    got, want, out = run_case(case, variant=VARIANTS[variant])
     f32 = bool(opts.get("f32"))
     rep = U.error_report(got, want, name, 2e-3 if f32 else 2e-2, 2e-3 if f32 else 2e-2)
     assert rep["bad_frac"] == 0 and rep["nan"] == 0, rep

@@ -16,6 +16,7 @@ LIB = os.path.join(PKG, "libtod.so")
 SOURCES = {
     "capi.cu": [],
     "conv_tcgen05.cu": [],
+    "conv_halo_tcgen05.cu": [],
     "stem_conv.cu": [],
     "sppf_pool.cu": [],
     "head_decode.cu": ["-fmad=false"],

@@ -1,0 +1,837 @@
+// Halo-patch implicit-GEMM convolution on tcgen05 / TMEM (sm_100a): the main conv kernel of libtod.so.
+//
+// Same contract as conv_tcgen05.cu (reference Conv.forward model/blocks.py:52-54 with fuse_conv :160-187 folded,
+// Bottleneck add :80-82, head 1x1 convs model/head.py:31,42, concat-by-offset), different data movement:
+//
+//   * A operand (activations).  tcgen05 shared-memory descriptors address rows as
+//         row(i) = start + (i / 8) * SBO + (i % 8) * row_bytes
+//     and the 128B/64B/32B swizzle is a function of the ABSOLUTE shared-memory address (measured:
+//     profiles/r1_probe_umma_rowshift.txt), so `start` may be shifted by whole rows and SBO may be any row multiple.
+//     A 3x3 conv therefore loads ONE (16+2) x (8+2) pixel halo patch per 64-channel chunk and issues its nine taps as
+//     nine descriptor views of that patch (tap (kh,kw): start += (kh*10 + kw) rows, SBO = 10 rows): L2->SM traffic for
+//     activations drops from 9x to 1.4x.  Stride 2 uses the four parity planes of the input the same way; 1x1 is the
+//     degenerate case (one tap, 128 consecutive pixels).
+//   * B operand (weights).  One weight tile [block_n x block_k] per (tap, chunk) feeds `m` M sub-tiles (m accumulators
+//     in TMEM); when the whole [block_n x K] weight panel fits in shared memory it is loaded once per CTA and stays
+//     resident across the persistent tile loop.
+//   * Epilogue.  TMEM -> registers -> bias / upsample-add / SiLU / residual -> swizzled staging panel in shared memory
+//     -> TMA store (clipped at the tensor edges, so partial tiles and channel windows need no guards).
+//
+// Warp roles (320 threads, 1 CTA / SM, persistent): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2..9 two epilogue groups that alternate over the two TMEM accumulator stages.
+#include <cstring>
+#include <mutex>
+
+#include "tma_host.cuh"
+
+namespace tod {
+
+constexpr int kHaloThreads = 320;
+constexpr int kMaxA = 4;      // A-ring slots
+constexpr int kMaxB = 40;     // B-ring slots (>= taps * chunks when the weights are resident)
+constexpr int kPatchH = 16, kPatchW = 8;
+constexpr uint32_t kStageBytes = 16384;              // one epilogue staging panel: 128 rows x 128 B
+constexpr uint32_t kHaloSmemLimit = 225u * 1024u;    // dynamic; static barriers + bias take < 2 KB of the 227 KB
+
+// n / d by multiplication: exact while n * d < 2^40 (checked on the host).  A runtime integer division is a ~40
+// instruction dependent chain, which a single-thread role (producer, MMA issuer) cannot afford per tile.
+struct FastDiv {
+  uint32_t d;
+  uint64_t mul;   // ceil(2^40 / d)
+  __device__ __forceinline__ int div(int n) const { return static_cast<int>((static_cast<uint64_t>(n) * mul) >> 40); }
+};
+
+struct __align__(64) HaloParams {
+  CUtensorMap tm_a[4];
+  CUtensorMap tm_w;
+  CUtensorMap tm_out;
+  // geometry
+  int patch_mode;            // 1: 16x8 pixel patches (3x3), 0: 128 consecutive pixels (1x1)
+  int hout, wout;
+  int tiles_w, tiles_per_img;
+  FastDiv fd_tiles_per_img, fd_tiles_w, fd_wout, fd_hw;
+  long long mtot;            // batch * hout * wout
+  int num_subtiles, m, num_super;
+  int n_tiles, block_n, cout;
+  int block_k, ksteps, chunks, num_taps;
+  // A loads per (sub-tile, chunk)
+  int n_aloads;
+  int al_map[4], al_dw[4], al_dh[4];
+  uint32_t al_off[4];
+  uint32_t a_tx_bytes;       // bytes landed per sub-tile per chunk
+  uint32_t b_tx_bytes;
+  uint32_t sub_bytes, a_slot_bytes, b_slot_bytes;
+  int sa, sb, stationary;
+  uint32_t tap_a_off[9];
+  uint32_t tap_hi_a[9];      // upper descriptor word per tap (SBO differs between parity planes)
+  uint32_t hi_b;
+  uint32_t idesc, tmem_cols;
+  uint32_t off_b, off_stage;
+  // epilogue
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const float* upadd;
+  int res_pitch;
+  int act, out_f32;
+  int pc, pb, smask;         // panel columns, panel row bytes, swizzle XOR mask (7 / 3 / 1)
+  unsigned long long* prof;  // optional per-CTA wait counters (tools/conv_profile.py), null in production
+};
+
+// Profiling helper: accumulates the cycles one role's single issuing thread spends inside a wait.
+struct WaitClock {
+  unsigned long long acc[4];
+  bool on;
+  __device__ __forceinline__ explicit WaitClock(bool enabled) : on(enabled) { acc[0] = acc[1] = acc[2] = acc[3] = 0; }
+  __device__ __forceinline__ long long begin() const { return on ? clock64() : 0; }
+  __device__ __forceinline__ void end(int i, long long t0) { if (on) acc[i] += clock64() - t0; }
+};
+
+__device__ __forceinline__ uint64_t halo_desc(uint32_t smem_addr, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | (1ull << 16) | ((smem_addr >> 4) & 0x3FFFu);
+}
+
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t smask) { return off ^ (((off >> 7) & smask) << 4); }
+
+struct RowCtx {
+  const float* bias_s;              // shared, indexed by column within the N tile
+  const float* up_ptr;              // global f32 row (already offset to n0) or null
+  const __nv_bfloat16* res_ptr;     // global bf16 row (already offset to n0) or null
+  int act;
+};
+
+// 16 accumulator columns [col, col+16) of this thread's row -> activation applied, in f[].
+__device__ __forceinline__ void epilogue_math16(const RowCtx& rc, const uint32_t* v, int col, float (&f)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(rc.bias_s + col + j);
+    f[j] = __uint_as_float(v[j]) + b.x;
+    f[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+    f[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+    f[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+  }
+  if (rc.up_ptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(rc.up_ptr + col + j));
+      f[j] += u.x; f[j + 1] += u.y; f[j + 2] += u.z; f[j + 3] += u.w;
+    }
+  }
+  if (rc.act == TOD_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+  }
+  if (rc.res_ptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rc.res_ptr + col + j));
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 rf = unpack_bf16x2(rw[t]);
+        f[j + 2 * t] += rf.x;
+        f[j + 2 * t + 1] += rf.y;
+      }
+    }
+  }
+}
+
+// ---- compact wait primitives.  Every role's steady-state code must stay small: one warp walking tens of KB of
+// unrolled code stalls on instruction fetch (measured: stall_no_inst dominated the MMA warp), so loops are kept rolled
+// and the cold timeout path is out of line.
+__device__ __noinline__ void halo_wait_timeout(uint32_t bar, uint32_t parity) {
+  printf("tod: conv_halo mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ bool try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void wait_addr(uint32_t bar, uint32_t parity) {
+  if (try_wait_addr(bar, parity)) return;
+  const long long t0 = clock64();
+#pragma unroll 1
+  while (!try_wait_addr(bar, parity))
+    if (clock64() - t0 > 4000000000ll) halo_wait_timeout(bar, parity);
+}
+// Up to four barriers at once (mask bit i enables bars[i]): the try_waits overlap instead of serialising ~100 cycles
+// each on the MMA issuer's critical path.
+__device__ __forceinline__ void wait_set(const uint32_t (&bars)[4], const uint32_t (&pars)[4], uint32_t mask) {
+  uint32_t pending = mask;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if ((pending >> i) & 1u)
+      if (try_wait_addr(bars[i], pars[i])) pending &= ~(1u << i);
+  if (pending == 0) return;
+  const long long t0 = clock64();
+#pragma unroll 1
+  while (pending != 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if ((pending >> i) & 1u)
+        if (try_wait_addr(bars[i], pars[i])) pending &= ~(1u << i);
+    if (clock64() - t0 > 4000000000ll) halo_wait_timeout(bars[0], pending);
+  }
+}
+
+// 16 accumulator columns of this thread's row: bias / upsample-add / SiLU / residual, then the 16-byte chunks go to the
+// swizzled staging panel.  col = column inside the N tile, pcol = column inside the panel.
+__device__ __forceinline__ void epilogue_store16(const RowCtx& rc, const uint32_t (&v)[16], int col, int pcol, uint32_t stage,
+                                                 uint32_t row_off, uint32_t smask, int out_f32) {
+  float f[16];
+  epilogue_math16(rc, v, col, f);
+  if (out_f32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t o = swz(row_off + (pcol * 4 + j * 16), smask);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + o), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                   "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t o = swz(row_off + (pcol * 2 + j * 16), smask);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + o), "r"(pack_bf16x2(f[8 * j], f[8 * j + 1])),
+                   "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])), "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
+                   "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
+                   : "memory");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
+  __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(16) float bias_s[256];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // persistent schedule: this CTA owns N tile `nt` and super-tiles first, first + step, ...
+  const int nt = blockIdx.x % p.n_tiles;
+  const int first = blockIdx.x / p.n_tiles;
+  const int step = gridDim.x / p.n_tiles;
+  const int n0 = nt * p.block_n;
+  const int acc_cols = p.m * p.block_n;   // TMEM columns of one accumulator stage
+  const uint32_t a_full0 = smem_u32(&a_full[0]), a_empty0 = smem_u32(&a_empty[0]);
+  const uint32_t b_full0 = smem_u32(&b_full[0]), b_empty0 = smem_u32(&b_empty[0]);   // barrier i lives at base + 8 * i
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a[0]);
+    tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_out);
+    for (int s = 0; s < p.sa; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.sb; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.block_n; i += kHaloThreads - 64)
+      bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.0f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
+      WaitClock wc(p.prof != nullptr);
+      const long long role_t0 = wc.begin();
+      if (p.stationary) {
+#pragma unroll 1
+        for (int c = 0; c < p.chunks; ++c)
+#pragma unroll 1
+          for (int t = 0; t < p.num_taps; ++t) {
+            const int i = c * p.num_taps + t;
+            mbar_arrive_expect_tx(&b_full[i], p.b_tx_bytes);
+            tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, (t * p.chunks + c) * p.block_k, n0);
+          }
+      }
+      int ai = 0, bi = 0;
+      uint32_t pha = 0, phb = 0;   // ring phase bits
+#pragma unroll 1
+      for (int st = first; st < p.num_super; st += step) {
+        const int s0 = st * p.m;
+        const int m_cur = min(p.m, p.num_subtiles - s0);
+#pragma unroll 1
+        for (int c = 0; c < p.chunks; ++c) {
+          long long tw = wc.begin();
+          wait_addr(a_empty0 + 8 * ai, pha ^ 1u);
+          wc.end(1, tw);
+          mbar_arrive_expect_tx(&a_full[ai], m_cur * p.a_tx_bytes);
+          const uint32_t slot = smem_base + ai * p.a_slot_bytes;
+#pragma unroll 1
+          for (int mt = 0; mt < m_cur; ++mt) {
+            const int s = s0 + mt;
+            int c1, c2, c3;
+            if (p.patch_mode) {
+              const int img = p.fd_tiles_per_img.div(s);
+              const int rem = s - img * p.tiles_per_img;
+              const int ti = p.fd_tiles_w.div(rem);
+              c1 = (rem - ti * p.tiles_w) * kPatchW;
+              c2 = ti * kPatchH;
+              c3 = img;
+            } else {
+              c1 = s * 128;
+              c2 = 0;
+              c3 = 0;
+            }
+#pragma unroll 1
+            for (int a = 0; a < p.n_aloads; ++a)
+              tma_load_4d(&p.tm_a[p.al_map[a]], &a_full[ai], slot + mt * p.sub_bytes + p.al_off[a], c * p.block_k,
+                          c1 + p.al_dw[a], c2 + p.al_dh[a], c3);
+          }
+          if (!p.stationary) {
+#pragma unroll 1
+            for (int t = 0; t < p.num_taps; ++t) {
+              tw = wc.begin();
+              wait_addr(b_empty0 + 8 * bi, phb ^ 1u);
+              wc.end(2, tw);
+              mbar_arrive_expect_tx(&b_full[bi], p.b_tx_bytes);
+              tma_load_2d(&p.tm_w, &b_full[bi], smem_base + p.off_b + bi * p.b_slot_bytes,
+                          (t * p.chunks + c) * p.block_k, n0);
+              if (++bi == p.sb) {
+                bi = 0;
+                phb ^= 1u;
+              }
+            }
+          }
+          if (++ai == p.sa) {
+            ai = 0;
+            pha ^= 1u;
+          }
+        }
+      }
+      if (p.prof) {
+        wc.end(0, role_t0);
+        for (int i = 0; i < 3; ++i) p.prof[blockIdx.x * 16 + i] = wc.acc[i];
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
+    uint32_t lt = 0;
+    int ai = 0, rbi = 0;
+    uint32_t pha = 0, phb = 0;
+    const uint32_t sub16 = p.sub_bytes >> 4;
+    const uint32_t b_ring = smem_base + p.off_b;
+    const int gsz = p.num_taps == 9 ? 3 : 1;   // taps per synchronisation group
+    const bool ks4 = p.ksteps == 4;
+    WaitClock wc(p.prof != nullptr && lane == 0);
+    const long long role_t0 = wc.begin();
+#pragma unroll 1
+    for (int st = first; st < p.num_super; st += step, ++lt) {
+      const int m_cur = min(p.m, p.num_subtiles - st * p.m);
+      const uint32_t acc = lt & 1;
+      long long tw = wc.begin();
+      wait_addr(smem_u32(&tmem_empty_bar[acc]), ((lt >> 1) & 1) ^ 1u);
+      wc.end(1, tw);
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * acc_cols;
+      const bool wait_b = !p.stationary || lt == 0;   // resident weights are only awaited on the first pass
+#pragma unroll 1
+      for (int c = 0; c < p.chunks; ++c) {
+        const uint32_t a_base = smem_base + ai * p.a_slot_bytes;
+#pragma unroll 1
+        for (int t0 = 0; t0 < p.num_taps; t0 += gsz) {
+          // one overlapped wait for the group's weight tiles (and the A slot at the start of a chunk) ...
+          uint32_t bars[4], pars[4];
+          int slot[3];
+          bars[0] = a_full0 + 8 * ai;
+          pars[0] = pha;
+          uint32_t mask = t0 == 0 ? 1u : 0u;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            slot[j] = 0;
+            bars[j + 1] = 0;
+            pars[j + 1] = 0;
+            if (j < gsz) {
+              if (p.stationary) {
+                slot[j] = c * p.num_taps + t0 + j;
+              } else {
+                slot[j] = rbi;
+                pars[j + 1] = phb;
+                if (++rbi == p.sb) {
+                  rbi = 0;
+                  phb ^= 1u;
+                }
+              }
+              bars[j + 1] = b_full0 + 8 * slot[j];
+              if (wait_b) mask |= 2u << j;
+            }
+          }
+          tw = wc.begin();
+          wait_set(bars, pars, mask);
+          wc.end(3, tw);
+          tcgen05_fence_after();
+          // ... then gsz * m * ksteps MMAs back to back
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              if (j < gsz) {
+                const int t = t0 + j;
+                const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
+                const uint32_t hi_a = p.tap_hi_a[t];
+                const uint32_t b_lo = umma_desc_lo(b_ring + slot[j] * p.b_slot_bytes);
+                const uint32_t accf = (c | t) != 0 ? 1u : 0u;
+#pragma unroll 1
+                for (int mt = 0; mt < m_cur; ++mt) {
+                  const uint32_t d_t = tmem_acc + mt * p.block_n;
+                  const uint32_t al = a_lo + mt * sub16;
+                  if (ks4) {
+                    umma_bf16_k4(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
+                  } else {
+#pragma unroll 1
+                    for (int k = 0; k < p.ksteps; ++k)
+                      umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, p.hi_b, p.idesc, accf | (k != 0 ? 1u : 0u));
+                  }
+                }
+                if (!p.stationary) umma_commit(&b_empty[slot[j]]);
+              }
+            }
+            if (t0 + gsz >= p.num_taps) {
+              umma_commit(&a_empty[ai]);
+              if (c == p.chunks - 1) umma_commit(&tmem_full_bar[acc]);
+            }
+          }
+          __syncwarp();
+        }
+        if (++ai == p.sa) {
+          ai = 0;
+          pha ^= 1u;
+        }
+      }
+    }
+    if (wc.on) {
+      wc.end(0, role_t0);
+      for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
+    const int group = (warp - 2) >> 2;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;            // accumulator row = pixel within the sub-tile
+    const bool leader = q == 0 && lane == 0;   // one thread per group issues the TMA stores
+    const uint32_t stage = smem_base + p.off_stage + group * kStageBytes;
+    const uint32_t bar_id = 1 + group;
+    const int npanels = ceil_div(p.block_n, p.pc);
+    const uint32_t row_off = static_cast<uint32_t>(r) * p.pb;
+    RowCtx rc;
+    rc.bias_s = bias_s;
+    rc.act = p.act;
+    WaitClock wc(p.prof != nullptr && leader);
+    const long long role_t0 = wc.begin();
+    uint32_t lt = 0;
+#pragma unroll 1
+    for (int st = first; st < p.num_super; st += step, ++lt) {
+      if ((lt & 1) != static_cast<uint32_t>(group)) continue;
+      const int s0 = st * p.m;
+      const int m_cur = min(p.m, p.num_subtiles - s0);
+      long long tw = wc.begin();
+      wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
+      wc.end(1, tw);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < m_cur; ++mt) {
+        const int s = s0 + mt;
+        int c1, c2, c3;
+        long long pix;
+        bool valid;
+        int h = 0, w = 0, img = 0;
+        if (p.patch_mode) {
+          img = p.fd_tiles_per_img.div(s);
+          const int rem = s - img * p.tiles_per_img;
+          const int ti = p.fd_tiles_w.div(rem);
+          c1 = (rem - ti * p.tiles_w) * kPatchW;
+          c2 = ti * kPatchH;
+          c3 = img;
+          h = c2 + (r >> 3);
+          w = c1 + (r & 7);
+          valid = h < p.hout && w < p.wout;
+          pix = (static_cast<long long>(img) * p.hout + h) * p.wout + w;
+        } else {
+          c1 = s * 128;
+          c2 = 0;
+          c3 = 0;
+          pix = static_cast<long long>(s) * 128 + r;
+          valid = pix < p.mtot;
+          if (p.upadd != nullptr) {   // only the upsample-add needs (img, h, w) of a flat pixel index
+            const int ipix = static_cast<int>(pix);
+            img = p.fd_hw.div(ipix);
+            const int rem = ipix - img * (p.hout * p.wout);
+            h = p.fd_wout.div(rem);
+            w = rem - h * p.wout;
+          }
+        }
+        rc.up_ptr = nullptr;
+        rc.res_ptr = nullptr;
+        if (valid) {
+          if (p.upadd)
+            rc.up_ptr = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
+          if (p.residual) rc.res_ptr = p.residual + pix * p.res_pitch + n0;
+        }
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
+#pragma unroll 1
+        for (int pn = 0; pn < npanels; ++pn) {
+          const int col0 = pn * p.pc;
+          const int ncols = min(p.pc, p.block_n - col0);
+          // the previous panel's TMA store must have finished reading the staging buffer
+          tw = wc.begin();
+          if (leader) bulk_wait_read_all();
+          named_bar_sync(bar_id, 128);
+          wc.end(2, tw);
+#pragma unroll 1
+          for (int c16 = 0; c16 < ncols; c16 += 32) {
+            uint32_t v0[16], v1[16];
+            const bool two = c16 + 16 < ncols;
+            tmem_ld_32x32b_x16(taddr0 + col0 + c16, v0);
+            if (two) tmem_ld_32x32b_x16(taddr0 + col0 + c16 + 16, v1);
+            tmem_ld_wait();
+            epilogue_store16(rc, v0, col0 + c16, c16, stage, row_off, p.smask, p.out_f32);
+            if (two) epilogue_store16(rc, v1, col0 + c16 + 16, c16 + 16, stage, row_off, p.smask, p.out_f32);
+          }
+          if (mt == m_cur - 1 && pn == npanels - 1) {
+            // last TMEM read of this accumulator stage: hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+          }
+          fence_proxy_async_smem();
+          tw = wc.begin();
+          named_bar_sync(bar_id, 128);
+          wc.end(3, tw);
+          if (leader) {
+            tma_store_4d(&p.tm_out, stage, n0 + col0, c1, c2, c3);
+            bulk_commit_group();
+          }
+        }
+      }
+    }
+    if (leader) bulk_wait_all();
+    if (wc.on) {
+      wc.end(0, role_t0);
+      for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 8 + group * 4 + i] = wc.acc[i];
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static unsigned long long* g_prof = nullptr;   // set by tod_debug_set_conv_profile (tools only)
+
+static uint32_t desc_hi(uint32_t sbo_bytes, int bk) {
+  const uint32_t layout_type = bk == 64 ? 2u : (bk == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+  return (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+}
+
+// Fills `p` for K-chunk width bk (cin_pad is fixed by the packed weights).  *fits = false when no shared-memory plan
+// exists for this bk (the caller retries with a narrower chunk).
+static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits) {
+  int rc;
+  *fits = true;
+  memset(&p, 0, sizeof(p));
+  const int hout = d->hin / d->stride, wout = d->win / d->stride;
+  const int taps = d->ksize * d->ksize;
+  const int k_total = taps * cin_pad;
+  const uint32_t rb = bk * 2;  // bytes per smem row
+  const CUtensorMapSwizzle swz_in =
+      bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const uint64_t px = static_cast<uint64_t>(d->x_pitch) * 2;
+  const long long mtot = static_cast<long long>(d->batch) * hout * wout;
+
+  p.hout = hout;
+  p.wout = wout;
+  p.mtot = mtot;
+  p.cout = d->cout;
+  p.block_k = bk;
+  p.ksteps = bk >> 4;
+  p.chunks = cin_pad / bk;
+  p.num_taps = taps;
+  p.n_tiles = ceil_div(d->cout, 256);
+  p.block_n = round_up(ceil_div(d->cout, p.n_tiles), 16);
+  p.b_tx_bytes = p.block_n * rb;
+  p.b_slot_bytes = round_up(p.block_n * rb, 1024);
+  p.hi_b = desc_hi(8 * rb, bk);
+
+  TOD_CHECK_ARG(mtot < (1ll << 31), "conv: too many output pixels");
+  // ---- A operand: tensor maps, loads per (sub-tile, chunk), per-tap descriptor views
+  uint32_t sub_bytes = 0;
+  if (d->ksize == 1) {
+    p.patch_mode = 0;
+    const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(mtot), 1, 1};
+    const uint64_t str[3] = {px, px * mtot, px * mtot};
+    const uint32_t box[4] = {static_cast<uint32_t>(bk), rows, 1, 1};
+    if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+    p.n_aloads = 1;
+    p.al_map[0] = 0;
+    p.a_tx_bytes = rows * rb;
+    p.tap_a_off[0] = 0;
+    p.tap_hi_a[0] = desc_hi(8 * rb, bk);
+    sub_bytes = 128 * rb;
+    p.num_subtiles = static_cast<int>((mtot + 127) / 128);
+    p.tiles_w = 1;
+    p.tiles_per_img = 1;
+  } else {
+    p.patch_mode = 1;
+    p.tiles_w = ceil_div(wout, kPatchW);
+    p.tiles_per_img = p.tiles_w * ceil_div(hout, kPatchH);
+    const long long nsub = static_cast<long long>(d->batch) * p.tiles_per_img;
+    TOD_CHECK_ARG(nsub < (1ll << 30), "conv: too many tiles");
+    p.num_subtiles = static_cast<int>(nsub);
+    if (d->stride == 1) {
+      const int pw = kPatchW + 2, ph = kPatchH + 2;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
+                                static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
+      const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(pw), static_cast<uint32_t>(ph), 1};
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+      p.n_aloads = 1;
+      p.al_map[0] = 0;
+      p.al_dw[0] = -1;
+      p.al_dh[0] = -1;
+      p.al_off[0] = 0;
+      p.a_tx_bytes = pw * ph * rb;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          p.tap_a_off[kh * 3 + kw] = (kh * pw + kw) * rb;
+          p.tap_hi_a[kh * 3 + kw] = desc_hi(pw * rb, bk);
+        }
+      sub_bytes = pw * ph * rb;
+    } else {
+      // input row 2*oh + kh - 1:  kh=0 -> plane row oh-1 of parity 1, kh=1 -> row oh of parity 0, kh=2 -> row oh of
+      // parity 1 (same for columns).  Parity-1 planes are loaded with one extra leading row / column.
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win / 2),
+                                static_cast<uint64_t>(d->hin / 2), static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {px * 2, px * d->win * 2, px * d->win * d->hin};
+      uint32_t plane_off[2][2];
+      int n = 0;
+      uint32_t off = 0;
+      p.a_tx_bytes = 0;
+      for (int ph = 1; ph >= 0; --ph)
+        for (int pw = 1; pw >= 0; --pw) {
+          const int bw = kPatchW + pw, bh = kPatchH + ph;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(d->d_x) + (static_cast<uint64_t>(ph) * d->win + pw) * px;
+          const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1};
+          if ((rc = encode_map(&p.tm_a[n], base, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+          p.al_map[n] = n;
+          p.al_dw[n] = -pw;
+          p.al_dh[n] = -ph;
+          p.al_off[n] = off;
+          plane_off[ph][pw] = off;
+          p.a_tx_bytes += bw * bh * rb;
+          off += round_up(bw * bh * rb, 1024);
+          ++n;
+        }
+      p.n_aloads = n;
+      sub_bytes = off;
+      const int par[3] = {1, 0, 1};
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ph = par[kh], pw = par[kw];
+          const int bw = kPatchW + pw;
+          const int ro = kh == 2 ? 1 : 0, co = kw == 2 ? 1 : 0;
+          p.tap_a_off[kh * 3 + kw] = plane_off[ph][pw] + (ro * bw + co) * rb;
+          p.tap_hi_a[kh * 3 + kw] = desc_hi(bw * rb, bk);
+        }
+    }
+  }
+  p.sub_bytes = round_up(sub_bytes, 1024);
+  {
+    auto make_fd = [](long long dd, long long nmax, FastDiv* f) {
+      f->d = static_cast<uint32_t>(dd);
+      f->mul = ((1ull << 40) + dd - 1) / dd;
+      return dd > 0 && nmax * dd < (1ll << 40);
+    };
+    const bool ok = make_fd(p.tiles_per_img, p.num_subtiles, &p.fd_tiles_per_img) &&
+                    make_fd(p.tiles_w, p.tiles_per_img, &p.fd_tiles_w) &&
+                    make_fd(wout, static_cast<long long>(hout) * wout, &p.fd_wout) &&
+                    (d->d_upadd == nullptr || make_fd(static_cast<long long>(hout) * wout, mtot, &p.fd_hw));
+    TOD_CHECK_ARG(ok, "conv: problem too large for the tile index arithmetic");
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(k_total), static_cast<uint64_t>(d->cout)};
+    const uint64_t str[1] = {static_cast<uint64_t>(k_total) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.block_n)};
+    if ((rc = encode_map(&p.tm_w, d->d_w, 2, dims, str, box, swz_in)) != TOD_OK) return rc;
+  }
+
+  // ---- output: staging panels of 128 rows x pb bytes, TMA store
+  p.out_f32 = d->out_dtype == TOD_OUT_F32;
+  const int esize = p.out_f32 ? 4 : 2;
+  int pc = 128 / esize;
+  while (pc > p.block_n) pc >>= 1;
+  if (p.n_tiles > 1)
+    while (p.block_n % pc) pc >>= 1;
+  p.pc = pc;
+  p.pb = pc * esize;
+  p.smask = p.pb >= 128 ? 7 : (p.pb == 64 ? 3 : 1);
+  TOD_CHECK_ARG(p.pb >= 32, "conv: output panel narrower than 32 bytes (cout %d)", d->cout);
+  {
+    const CUtensorMapSwizzle swz_out =
+        p.pb >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapDataType dt = p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const uint64_t opx = static_cast<uint64_t>(d->out_pitch) * esize;
+    if (p.patch_mode) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(wout), static_cast<uint64_t>(hout),
+                                static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {opx, opx * wout, opx * wout * hout};
+      const uint32_t box[4] = {static_cast<uint32_t>(pc), kPatchW, kPatchH, 1};
+      if ((rc = encode_map(&p.tm_out, d->d_out, 4, dims, str, box, swz_out, dt)) != TOD_OK) return rc;
+    } else {
+      const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(mtot), 1, 1};
+      const uint64_t str[3] = {opx, opx * mtot, opx * mtot};
+      const uint32_t box[4] = {static_cast<uint32_t>(pc), rows, 1, 1};
+      if ((rc = encode_map(&p.tm_out, d->d_out, 4, dims, str, box, swz_out, dt)) != TOD_OK) return rc;
+    }
+  }
+
+  // ---- shared-memory plan: m sub-tiles per weight tile, A ring, B ring or resident weights
+  const uint32_t staging = 2 * kStageBytes;
+  const uint32_t budget = kHaloSmemLimit - 1024 - staging;
+  const uint32_t b_total = static_cast<uint32_t>(taps) * p.chunks * p.b_slot_bytes;
+  const bool may_station = taps * p.chunks <= kMaxB && d->reserved[2] != 1;
+  int m_max = 512 / (2 * p.block_n);
+  if (m_max > 4) m_max = 4;
+  if (m_max < 1) m_max = 1;
+  if (m_max > p.num_subtiles) m_max = p.num_subtiles;
+  if (d->reserved[1] > 0 && d->reserved[1] < m_max) m_max = d->reserved[1];
+  double best_cost = -1.0;
+  for (int m = m_max; m >= 1; --m) {
+    const uint32_t a_slot = m * p.sub_bytes;
+    for (int stn = 1; stn >= 0; --stn) {
+      int sa, sb;
+      if (stn) {
+        if (!may_station || b_total + 2 * a_slot > budget) continue;
+        sb = taps * p.chunks;
+        sa = static_cast<int>((budget - b_total) / a_slot);
+      } else {
+        const int sb_min = taps >= 3 ? 3 : 2;
+        uint32_t used = 2 * a_slot + sb_min * p.b_slot_bytes;
+        if (used > budget) continue;
+        sa = 2;
+        sb = sb_min;
+        // grow whichever ring currently gives the shorter look-ahead (an A slot lasts `taps` weight tiles)
+        for (;;) {
+          const bool grow_a = (sa - 1) * taps <= (sb - 1);
+          if (grow_a && sa < kMaxA && used + a_slot <= budget) {
+            ++sa;
+            used += a_slot;
+          } else if (sb < kMaxB && used + p.b_slot_bytes <= budget) {
+            ++sb;
+            used += p.b_slot_bytes;
+          } else if (!grow_a && sa < kMaxA && used + a_slot <= budget) {
+            ++sa;
+            used += a_slot;
+          } else {
+            break;
+          }
+        }
+      }
+      if (sa > kMaxA) sa = kMaxA;
+      if (sb > kMaxB) sb = kMaxB;
+      // L2 -> SM bytes per output pixel
+      const double cost = (static_cast<double>(p.a_tx_bytes) * p.chunks + (stn ? 0.0 : static_cast<double>(b_total) / m)) / 128.0;
+      if (best_cost < 0 || cost < best_cost * 0.98) {
+        best_cost = cost;
+        p.m = m;
+        p.sa = sa;
+        p.sb = sb;
+        p.stationary = stn;
+      }
+    }
+  }
+  if (best_cost < 0) {
+    *fits = false;
+    return TOD_OK;
+  }
+  if (d->num_stages > 0 && d->num_stages < p.sa) p.sa = d->num_stages;
+  p.a_slot_bytes = p.m * p.sub_bytes;
+  p.off_b = p.sa * p.a_slot_bytes;
+  p.off_stage = p.off_b + p.sb * p.b_slot_bytes;
+  const size_t smem = static_cast<size_t>(p.off_stage) + staging + 1024;
+  TOD_CHECK_ARG(smem <= kHaloSmemLimit, "conv: shared-memory plan overflows (%zu bytes)", smem);
+  p.num_super = ceil_div(p.num_subtiles, p.m);
+
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * p.m * p.block_n)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  p.bias = d->d_bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
+  p.upadd = d->d_upadd;
+  p.res_pitch = d->res_pitch;
+  p.act = d->act;
+  p.prof = g_prof;
+  *smem_bytes = smem;
+  return TOD_OK;
+}
+
+int conv_halo_launch(const tod_conv_desc* d, void* stream) {
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_halo_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit);
+  });
+  int rc;
+  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_halo_tcgen05)")) != TOD_OK) return rc;
+
+  HaloParams p;
+  size_t smem = 0;
+  bool fits = false;
+  const int bk0 = pick_block_k(d->cin, d->block_k);
+  const int cin_pad = round_up(d->cin, bk0);
+  for (int bk = bk0; bk >= 16 && !fits; bk >>= 1)
+    if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits)) != TOD_OK) return rc;
+  TOD_CHECK_ARG(fits, "conv: no shared-memory plan fits (cin %d cout %d ksize %d stride %d)", d->cin, d->cout, d->ksize,
+                d->stride);
+
+  const long long work = static_cast<long long>(p.num_super) * p.n_tiles;
+  long long grid = num_sms();
+  if (grid > work) grid = work;
+  grid -= grid % p.n_tiles;
+  if (grid < p.n_tiles) grid = p.n_tiles;
+  conv_halo_tcgen05<<<static_cast<unsigned>(grid), kHaloThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  TOD_CHECK_LAUNCH("conv_halo_tcgen05 launch");
+  return TOD_OK;
+}
+
+}  // namespace tod
+
+// Tools only: d_buf (>= 16 * 8 bytes per CTA, 148 CTAs) receives per-CTA wait-cycle counters of the next conv launches:
+// [0..2] producer total / wait A-empty / wait B-empty, [3..6] MMA total / wait TMEM-empty / wait A-full / wait B-full,
+// [8..11] epilogue group 0 total / wait TMEM-full / wait staging free / wait panel written, [12..15] group 1.
+extern "C" int tod_debug_set_conv_profile(void* d_buf) {
+  tod::g_prof = reinterpret_cast<unsigned long long*>(d_buf);
+  return TOD_OK;
+}

@@ -16,7 +16,7 @@
 #include <cstring>
 #include <mutex>
 
-#include "tod_common.cuh"
+#include "tma_host.cuh"
 
 namespace tod {
 
@@ -152,9 +152,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
-      uint32_t it = 0;  // ring position, continues across tiles
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
+      int s = 0;         // ring slot and phase, continue across tiles
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles;
         const int n0 = (tile - mt * p.n_tiles) * p.block_n;
@@ -163,46 +164,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
         const int tile_h = trem / p.tiles_w;
         const int h0 = tile_h * p.th;
         const int w0 = (trem - tile_h * p.tiles_w) * p.tw;
-        for (int i = 0; i < num_chunks; ++i, ++it) {
-          const int s = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
-          const int tap = i / p.chunks_per_tap;
-          const int cc = i - tap * p.chunks_per_tap;
-          const uint32_t sa = smem_base + s * stage_bytes;
-          tma_load_4d(&p.tm_a[p.tap_map[tap]], &full_bar[s], sa, cc * p.block_k, w0 + p.tap_dw[tap],
-                      h0 + p.tap_dh[tap], img);
-          tma_load_2d(&p.tm_w, &full_bar[s], sa + p.stage_a_bytes, i * p.block_k, n0);
-        }
+        int i = 0;
+        for (int tap = 0; tap < p.num_taps; ++tap)
+          for (int cc = 0; cc < p.chunks_per_tap; ++cc, ++i) {
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
+            const uint32_t sa = smem_base + s * stage_bytes;
+            tma_load_4d(&p.tm_a[p.tap_map[tap]], &full_bar[s], sa, cc * p.block_k, w0 + p.tap_dw[tap],
+                        h0 + p.tap_dh[tap], img);
+            tma_load_2d(&p.tm_w, &full_bar[s], sa + p.stage_a_bytes, i * p.block_k, n0);
+            if (++s == p.num_stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one lane issues)
     const int ksteps = p.block_k >> 4;  // UMMA_K = 16 for bf16
-    uint32_t it = 0, lt = 0;            // ring position, local tile index
+    uint32_t lt = 0;                    // local tile index
+    int s = 0;                          // ring slot and phase
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const uint32_t acc = lt & 1;
       mbar_wait(&tmem_empty_bar[acc], ((lt >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator stage
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * p.block_n;
-      for (int i = 0; i < num_chunks; ++i, ++it) {
-        const int s = it % p.num_stages;
-        const uint32_t ph = (it / p.num_stages) & 1;
+      for (int i = 0; i < num_chunks; ++i) {
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_base + s * stage_bytes;
-          const uint64_t da = make_smem_desc(sa, p.desc_hi);
-          const uint64_t db = make_smem_desc(sa + p.stage_a_bytes, p.desc_hi);
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (i | k) != 0 ? 1u : 0u);
-          }
+          const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + p.stage_a_bytes);
+          // K steps of 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field per step
+          if (ksteps == 4)
+            umma_bf16_k4(tmem_d, a_lo, p.desc_hi, b_lo, p.desc_hi, p.idesc, i != 0 ? 1u : 0u);
+          else if (ksteps == 2)
+            umma_bf16_k2(tmem_d, a_lo, p.desc_hi, b_lo, p.desc_hi, p.idesc, i != 0 ? 1u : 0u);
+          else
+            umma_bf16_k1(tmem_d, a_lo, p.desc_hi, b_lo, p.desc_hi, p.idesc, i != 0 ? 1u : 0u);
           umma_commit(&empty_bar[s]);                               // smem slot free once these MMAs retire
           if (i == num_chunks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
         __syncwarp();
+        if (++s == p.num_stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else {
@@ -315,71 +324,6 @@ __global__ void conv_simt_check(const SimtParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  });
-  return fn;
-}
-
-static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, CUtensorMapSwizzle swz) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return TOD_ERR_CUDA;
-  }
-  cuuint64_t gdim[5];
-  cuuint64_t gstr[4];
-  cuuint32_t bdim[5], estr[5];
-  for (int i = 0; i < rank; ++i) {
-    gdim[i] = dims[i];
-    bdim[i] = box[i];
-    estr[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
-  }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] "
-              "stride0 %llu base %p",
-              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
-              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
-              rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, (unsigned long long)strides_bytes[0], base);
-    return TOD_ERR_CUDA;
-  }
-  return TOD_OK;
-}
-
-static int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0)
-      sms = 148;
-  }
-  return sms;
-}
-
-static int pick_block_k(int cin, int hint) {
-  if (hint == 16 || hint == 32 || hint == 64) return hint;
-  if (cin % 64 == 0) return 64;
-  if (cin % 32 == 0) return 32;
-  return 16;
-}
-
 // patch shape minimising the number of 128-row tiles for an hout x wout map
 static void pick_patch(int hout, int wout, int* th, int* tw) {
   long long best = -1;
@@ -442,6 +386,8 @@ extern "C" int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_
 extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   int rc = validate(d);
   if (rc != TOD_OK) return rc;
+  // reserved[0]: kernel variant -- 0 auto, 1 per-tap loads (this file), 2 halo patches (conv_halo_tcgen05.cu)
+  if (d->reserved[0] != 1) return conv_halo_launch(d, stream);
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
