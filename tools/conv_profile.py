@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--filter", default="")
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--no-station", action="store_true")
+    ap.add_argument("--trace", type=int, default=0, help="print the first N entries of CTA 0's MMA-group timeline")
     a = ap.parse_args()
     C_, d, m = synth.SCALES[a.scale]
     model = BaseModel(80, C_, d, m).eval()
@@ -41,7 +42,7 @@ def main():
     torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
     L = eng.L
-    prof = torch.zeros((148, 16), dtype=torch.int64, device="cuda")
+    prof = torch.zeros((148 * 16 + 3 * 1024 + 8,), dtype=torch.int64, device="cuda")
     filt = [f for f in a.filter.split(",") if f]
     for kind, name, payload in eng.ops:
         if kind != "conv" or (filt and not any(f in name for f in filt)):
@@ -58,7 +59,8 @@ def main():
         torch.cuda.synchronize()
         check(L.tod_debug_set_conv_profile(None), "clear profile")
         ms = e0.elapsed_time(e1)
-        pr = prof.cpu().numpy().astype(np.float64)
+        raw = prof.cpu().numpy()
+        pr = raw[:148 * 16].reshape(148, 16).astype(np.float64)
         used = pr[:, 3] > 0
         avg = pr[used].mean(0)
         dd = payload
@@ -69,6 +71,13 @@ def main():
             if nm == "-" or nm.endswith(".total"):
                 continue
             print(f"   {nm:26s} {avg[i]:10.0f} cyc  {100 * avg[i] / tot:5.1f}% of mma-role time")
+        if a.trace:
+            n = int(raw[148 * 16 + 3 * 1024])
+            tr = raw[148 * 16:148 * 16 + 3 * n].reshape(n, 3)
+            print(f"   CTA 0 timeline, {n} groups: [wait start, ready, issue end] -> wait, issue, gap to next group")
+            for i in range(min(n, a.trace)):
+                nxt = tr[i + 1, 0] - tr[i, 2] if i + 1 < n else 0
+                print(f"     g{i:3d} t={tr[i, 0]:8d} wait {tr[i, 1] - tr[i, 0]:6d} issue {tr[i, 2] - tr[i, 1]:6d} gap {nxt:6d}")
 
 
 if __name__ == "__main__":

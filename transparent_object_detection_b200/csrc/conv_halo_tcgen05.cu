@@ -100,25 +100,31 @@ struct RowCtx {
 };
 
 // 16 accumulator columns [col, col+16) of this thread's row -> activation applied, in f[].
+// With SiLU the bias in shared memory is pre-halved: h = acc / 2 + b / 2 is one FMA, silu = h + h * tanh(h).
 __device__ __forceinline__ void epilogue_math16(const RowCtx& rc, const uint32_t* v, int col, float (&f)[16]) {
+  const bool silu = rc.act == TOD_ACT_SILU;
+  const float sc = silu ? 0.5f : 1.0f;
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(rc.bias_s + col + j);
-    f[j] = __uint_as_float(v[j]) + b.x;
-    f[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-    f[j + 2] = __uint_as_float(v[j + 2]) + b.z;
-    f[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+    f[j] = fmaf(__uint_as_float(v[j]), sc, b.x);
+    f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc, b.y);
+    f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc, b.z);
+    f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc, b.w);
   }
   if (rc.up_ptr) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
       const float4 u = __ldg(reinterpret_cast<const float4*>(rc.up_ptr + col + j));
-      f[j] += u.x; f[j + 1] += u.y; f[j + 2] += u.z; f[j + 3] += u.w;
+      f[j] = fmaf(u.x, sc, f[j]);
+      f[j + 1] = fmaf(u.y, sc, f[j + 1]);
+      f[j + 2] = fmaf(u.z, sc, f[j + 2]);
+      f[j + 3] = fmaf(u.w, sc, f[j + 3]);
     }
   }
-  if (rc.act == TOD_ACT_SILU) {
+  if (silu) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+    for (int j = 0; j < 16; ++j) f[j] = silu_from_half(f[j]);
   }
   if (rc.res_ptr) {
 #pragma unroll
@@ -160,11 +166,11 @@ __device__ __forceinline__ void wait_addr(uint32_t bar, uint32_t parity) {
 // Up to four barriers at once (mask bit i enables bars[i]): the try_waits overlap instead of serialising ~100 cycles
 // each on the MMA issuer's critical path.
 __device__ __forceinline__ void wait_set(const uint32_t (&bars)[4], const uint32_t (&pars)[4], uint32_t mask) {
-  uint32_t pending = mask;
+  uint32_t ready = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if ((pending >> i) & 1u)
-      if (try_wait_addr(bars[i], pars[i])) pending &= ~(1u << i);
+  for (int i = 0; i < 4; ++i)   // independent of one another: the four try_waits are in flight together
+    if ((mask >> i) & 1u) ready |= static_cast<uint32_t>(try_wait_addr(bars[i], pars[i])) << i;
+  uint32_t pending = mask & ~ready;
   if (pending == 0) return;
   const long long t0 = clock64();
 #pragma unroll 1
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.block_n; i += kHaloThreads - 64)
-      bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.0f;
+      bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) * (p.act == TOD_ACT_SILU ? 0.5f : 1.0f) : 0.0f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -341,6 +347,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const bool ks4 = p.ksteps == 4;
     WaitClock wc(p.prof != nullptr && lane == 0);
     const long long role_t0 = wc.begin();
+    const bool trace = wc.on && blockIdx.x == 0;   // CTA 0 also records a per-group timeline
+    int ntrace = 0;
 #pragma unroll 1
     for (int st = first; st < p.num_super; st += step, ++lt) {
       const int m_cur = min(p.m, p.num_subtiles - st * p.m);
@@ -357,34 +365,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
 #pragma unroll 1
         for (int t0 = 0; t0 < p.num_taps; t0 += gsz) {
           // one overlapped wait for the group's weight tiles (and the A slot at the start of a chunk) ...
-          uint32_t bars[4], pars[4];
-          int slot[3];
-          bars[0] = a_full0 + 8 * ai;
-          pars[0] = pha;
-          uint32_t mask = t0 == 0 ? 1u : 0u;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            slot[j] = 0;
-            bars[j + 1] = 0;
-            pars[j + 1] = 0;
-            if (j < gsz) {
-              if (p.stationary) {
-                slot[j] = c * p.num_taps + t0 + j;
-              } else {
-                slot[j] = rbi;
-                pars[j + 1] = phb;
-                if (++rbi == p.sb) {
-                  rbi = 0;
-                  phb ^= 1u;
-                }
-              }
-              bars[j + 1] = b_full0 + 8 * slot[j];
-              if (wait_b) mask |= 2u << j;
+          // (the host makes the ring size a multiple of gsz, so a group's slots are consecutive and share a phase)
+          int slot0;
+          uint32_t par_b = 0;
+          if (p.stationary) {
+            slot0 = c * p.num_taps + t0;
+          } else {
+            slot0 = rbi;
+            par_b = phb;
+            rbi += gsz;
+            if (rbi == p.sb) {
+              rbi = 0;
+              phb ^= 1u;
             }
           }
+          uint32_t bars[4], pars[4];
+          bars[0] = a_full0 + 8 * ai;
+          pars[0] = pha;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            bars[j + 1] = b_full0 + 8 * (slot0 + j);
+            pars[j + 1] = par_b;
+          }
+          const uint32_t mask = (t0 == 0 ? 1u : 0u) | (wait_b ? (gsz == 3 ? 14u : 2u) : 0u);
           tw = wc.begin();
           wait_set(bars, pars, mask);
           wc.end(3, tw);
+          const long long t_ready = trace ? clock64() : 0;
           tcgen05_fence_after();
           // ... then gsz * m * ksteps MMAs back to back
           if (elect_one()) {
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
                 const int t = t0 + j;
                 const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
                 const uint32_t hi_a = p.tap_hi_a[t];
-                const uint32_t b_lo = umma_desc_lo(b_ring + slot[j] * p.b_slot_bytes);
+                const uint32_t b_lo = umma_desc_lo(b_ring + (slot0 + j) * p.b_slot_bytes);
                 const uint32_t accf = (c | t) != 0 ? 1u : 0u;
 #pragma unroll 1
                 for (int mt = 0; mt < m_cur; ++mt) {
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
                       umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, p.hi_b, p.idesc, accf | (k != 0 ? 1u : 0u));
                   }
                 }
-                if (!p.stationary) umma_commit(&b_empty[slot[j]]);
+                if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
               }
             }
             if (t0 + gsz >= p.num_taps) {
@@ -417,6 +424,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
             }
           }
           __syncwarp();
+          if (trace && ntrace < 1024) {
+            unsigned long long* tr = p.prof + 148 * 16 + 3 * ntrace;
+            tr[0] = tw - role_t0;
+            tr[1] = t_ready - role_t0;
+            tr[2] = clock64() - role_t0;
+            ++ntrace;
+          }
         }
         if (++ai == p.sa) {
           ai = 0;
@@ -427,6 +441,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     if (wc.on) {
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
+      if (trace) p.prof[148 * 16 + 3 * 1024] = ntrace;
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
@@ -759,6 +774,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
       }
       if (sa > kMaxA) sa = kMaxA;
       if (sb > kMaxB) sb = kMaxB;
+      if (!stn && taps == 9) sb -= sb % 3;   // the MMA issuer consumes weight tiles in groups of three consecutive slots
       // L2 -> SM bytes per output pixel
       const double cost = (static_cast<double>(p.a_tx_bytes) * p.chunks + (stn ? 0.0 : static_cast<double>(b_total) / m)) / 128.0;
       if (best_cost < 0 || cost < best_cost * 0.98) {
