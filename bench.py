@@ -9,7 +9,7 @@ One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); every rank runs 
   value        whole-job images/s with the batch already resident in HBM (CUDA-graph replay of
                network + decode + NMS), device-timed, max over ranks
   e2e          same metric through Detector.detect: pinned host float32 batch -> H2D -> graph -> D2H of detections
-  roofline     the dominant kernel (conv_igemm_tcgen05, all conv launches of one pass) against the measured
+  roofline     the dominant kernel (conv_halo_tcgen05, all conv launches of one pass) against the measured
                bf16 tensor peak: algorithmic conv FLOPs / summed conv launch time (CUDA events, eager pass)
   cpu_baseline the CPU oracle (port of the reference path) on this box's host cores, bounded sample
   --impl reference   times the CPU oracle alone (the reference itself cannot travel to the GPU box)
@@ -268,8 +268,15 @@ def main():
         all_ms = sum(r["ms"] for r in table)
         achieved = conv_gflop / conv_ms if conv_ms > 0 else 0.0          # TFLOP/s (GFLOP / ms)
         peak = pk["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv_igemm_tcgen05", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+        traffic = None                                     # DRAM bytes per conv launch from the committed ncu pass
+        tpath = os.path.join(ROOT, "profiles", "conv_dram_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = float(json.load(open(tpath))["avg_bytes_per_launch"])
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "kernel": "conv_halo_tcgen05", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                 "launches": len(conv_rows), "flop_per_launch_avg": conv_gflop * 1e9 / max(len(conv_rows), 1),
                 "avg_launch_ms": conv_ms / max(len(conv_rows), 1), "conv_share_of_eager_pass": conv_ms / all_ms if all_ms else None}
         cpu = None

@@ -9,8 +9,8 @@ restatement is pinned against the reference's OWN code executed in the authoring
 (oracle/make_golden.py imports /root/reference and writes tests/golden/*.npz; the
 `-m "not gpu"` tests compare this file with those fixtures).  Third-party arithmetic on the
 path: torchvision.ops.nms (unpinned by the reference; fixtures generated with
-torchvision 0.26.0+cu128 CPU kernel) -- restated in `nms_greedy` below and in
-oracle/nms_oracle.c.
+torchvision 0.26.0+cu128 CPU kernel) -- restated in `nms_greedy` below and, in plain C, in
+oracle/nms_oracle.c (built by oracle/Makefile, wrapped by oracle/nms_c.py).
 
 Every function cites the reference file:line it follows.  Weights come in as a dict with
 the reference's state_dict key layout (oracle/synth.py:state_dict_shapes).
@@ -258,13 +258,14 @@ def nms_keep_indices(prediction: np.ndarray, num_classes: int, conf_thres: float
 
 
 def non_max_suppression(prediction: np.ndarray, num_classes: int, input_shape, image_shape,
-                        letterbox_image: bool, conf_thres: float = 0.5, nms_thres: float = 0.4
-                        ) -> List[Optional[np.ndarray]]:
+                        letterbox_image: bool, conf_thres: float = 0.5, nms_thres: float = 0.4,
+                        keep_fn=None) -> List[Optional[np.ndarray]]:
     """reference DecodeBox.non_max_suppression, utils/bbox_utils.py:119-182.
 
     Like the reference it rewrites prediction[:, :, :4] to corner form IN PLACE (:144-149) and
-    returns, per image, None or float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] in image pixels."""
-    keep = nms_keep_indices(prediction, num_classes, conf_thres, nms_thres)
+    returns, per image, None or float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] in image pixels.
+    `keep_fn` swaps the selection step for another restatement with the same contract (oracle/nms_c.py)."""
+    keep = (keep_fn or nms_keep_indices)(prediction, num_classes, conf_thres, nms_thres)
     half = np.float32(2)
     xywh = prediction[:, :, :4].copy()
     prediction[:, :, 0] = xywh[:, :, 0] - xywh[:, :, 2] / half

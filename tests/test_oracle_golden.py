@@ -148,3 +148,32 @@ def test_config1_scale_s_640(golden):
     assert out.shape == (1, 84, 8400)
     np.testing.assert_allclose(out.numpy()[:, :, ::16], g["out_sub"], rtol=1e-4, atol=2e-4)
     np.testing.assert_allclose(out.numpy().astype(np.float64).sum(), float(g["out_sum"]), rtol=1e-6)
+
+
+# ---------------------------------------------------------------- plain-C restatement (oracle/nms_oracle.c)
+@pytest.mark.parametrize("tag,conf,iou", [("coco", 0.001, 0.65), ("cb", 0.05, 0.5), ("default", 0.5, 0.4)])
+def test_c_oracle_dense_nms_bit_exact(golden, tag, conf, iou):
+    from oracle import nms_c
+    g = golden("nms_cases.npz")
+    pred = synth.make_dense_predictions(2, anchors=700, nc=80, objects=24, seed=1234)
+    got = O.non_max_suppression(pred, 80, (640, 640), (480, 640), True, conf, iou, keep_fn=nms_c.nms_keep_indices)
+    assert_dets_equal(got, unpack(g[f"dense_{tag}_rows"], g[f"dense_{tag}_counts"]))
+
+
+def test_c_oracle_adversarial_nms_bit_exact(golden):
+    from oracle import nms_c
+    g = golden("nms_cases.npz")
+    names = sorted({k[4:-5] for k in g.files if k.startswith("adv_") and k.endswith("_pred")})
+    for name in names:
+        conf, iou = g[f"adv_{name}_thr"]
+        got = O.non_max_suppression(g[f"adv_{name}_pred"].copy(), 4, (1, 1), (1, 1), False, float(conf), float(iou),
+                                    keep_fn=nms_c.nms_keep_indices)
+        assert_dets_equal(got, unpack(g[f"adv_{name}_rows"], g[f"adv_{name}_counts"]))
+
+
+def test_c_oracle_matches_numpy_oracle_at_full_size():
+    from oracle import nms_c
+    pred = synth.make_dense_predictions(2, anchors=8400, nc=80, objects=120, seed=1234)
+    a = nms_c.nms_keep_indices(pred, 80, 0.001, 0.65)
+    b = O.nms_keep_indices(pred, 80, 0.001, 0.65)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 100

@@ -1,0 +1,86 @@
+"""N>1 path on CPU: world_size-2 gloo processes shard a synthetic image range, post-process their share with the
+oracle's NMS (the GPU kernels are not involved here) and gather on rank 0; the gathered list must equal the
+single-process result exactly and arrive in rank order."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rows_for(images):
+    from oracle import detector_oracle as O, synth
+    out = []
+    for i in images:
+        pred = synth.make_dense_predictions(1, anchors=300, nc=8, objects=6, seed=100 + i)
+        if i % 5 == 3:
+            pred[..., 4:] = 0.0                      # an image without candidates -> None
+        out.extend(O.non_max_suppression(pred, 8, (64, 64), (48, 64), True, 0.05, 0.5))
+    return out
+
+
+def _worker(rank, world, port, n_images, q):
+    sys.path.insert(0, ROOT)
+    from transparent_object_detection_b200.sharding import gather_detections, shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(n_images, rank, world)
+    got = gather_detections(_rows_for(range(lo, hi)))
+    if rank == 0:
+        q.put([None if r is None else r.copy() for r in got])
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_tile_the_batch():
+    from transparent_object_detection_b200.sharding import shard_range
+    for n in (0, 1, 7, 64, 4096):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def test_gather_without_process_group_is_identity():
+    from transparent_object_detection_b200.sharding import gather_detections
+    rows = [None, np.ones((2, 6), np.float32)]
+    got = gather_detections(rows)
+    assert got[0] is None and np.array_equal(got[1], rows[1])
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_gather_equals_single_process():
+    n_images, world = 11, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_images, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=100)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _rows_for(range(n_images))
+    assert len(got) == len(want) == n_images
+    assert any(w is None for w in want) and any(w is not None for w in want)
+    for g, w in zip(got, want):
+        assert (g is None) == (w is None)
+        if w is not None:
+            assert g.dtype == np.float32 and np.array_equal(g, w)
