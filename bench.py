@@ -6,9 +6,11 @@
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); every rank runs the same batch-sharded work
 (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
 
-  value        whole-job images/s with the batch already resident in HBM (CUDA-graph replay of
+  value        whole-job images/s with the uint8 image batch already resident in HBM (CUDA-graph replay of
                network + decode + NMS), device-timed, max over ranks
-  e2e          same metric through Detector.detect: pinned host float32 batch -> H2D -> graph -> D2H of detections
+  e2e          same metric through the public API Detector.submit / Detector.collect (two batches in flight): pinned
+               host uint8 (B, H, W, 3) batch -> H2D -> graph -> D2H of counts and kept rows, every step;
+               e2e.f32_input is the synchronous Detector.detect on the reference's float32 (B, 3, H, W) tensor
   roofline     the dominant kernel (conv_halo_tcgen05, all conv launches of one pass) against the measured
                bf16 tensor peak: algorithmic conv FLOPs / summed conv launch time (CUDA events, eager pass)
   cpu_baseline the CPU oracle (port of the reference path) on this box's host cores, bounded sample
@@ -89,7 +91,7 @@ def cpu_oracle_rate(scale: str, size: int, images: int, min_seconds: float, max_
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()}
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    x = torch.from_numpy(synth.make_images(images, size, size, seed=3))
+    x = torch.from_numpy(synth.images_u8_to_f32(synth.make_images_u8(images, size, size, seed=3)))
     O.detect(sd, x[:1], 80, d, (size, size), True, CONF, IOU)          # warm-up
     times = []
     t_all = time.perf_counter()
@@ -110,7 +112,7 @@ def run_reference(args, rank, world):
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()}
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    x = torch.from_numpy(synth.make_images(images, args.size, args.size, seed=3))
+    x = torch.from_numpy(synth.images_u8_to_f32(synth.make_images_u8(images, args.size, args.size, seed=3)))
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         O.detect(sd, x, 80, d, (args.size, args.size), True, CONF, IOU)
@@ -165,10 +167,11 @@ def main():
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
     det = Detector(model, (args.size, args.size), confidence=CONF, nms_iou=IOU, letterbox_image=True)
     B = args.batch
-    # rank-distinct synthetic batches (seed 3 + rank), two pinned host copies for the e2e leg
-    hosts = [torch.from_numpy(synth.make_images(B, args.size, args.size, seed=3 + 17 * rank + j)).pin_memory() for j in range(2)]
-    eng = det._engine(B, dev)
-    eng.x_static.copy_(hosts[0])
+    # rank-distinct synthetic uint8 batches (seed 3 + 17*rank + j), two pinned host copies for the e2e leg
+    hosts = [torch.from_numpy(synth.make_images_u8(B, args.size, args.size, seed=3 + 17 * rank + j)).pin_memory() for j in range(2)]
+    eng = model.engine(B, args.size, args.size, dev)
+    graph = eng.graph_for("u8", 0, CONF, IOU)
+    eng.input_buffer("u8", 0).copy_(hosts[0])
     torch.cuda.synchronize()
 
     def barrier():
@@ -179,43 +182,52 @@ def main():
     sampler = ClockSampler(local_rank)
     # ---------------------------------------------------------------- device-resident throughput
     for _ in range(args.warmup):
-        eng.replay()
+        graph.replay()
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.replay()
+        graph.replay()
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    # ---------------------------------------------------------------- end to end (host buffers)
-    for j in range(2):
-        det.detect(hosts[j])
+    # ---------------------------------------------------------------- end to end (host buffers, public API, 2 in flight)
+    for j in range(max(args.warmup, 2)):
+        det.detect(hosts[j & 1])
     barrier()
     d2h = 0
     t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(args.steps):
-        eng2 = det.detect_device(hosts[i & 1])
-        counts = eng2.keep_count.cpu()
-        mx = int(counts.max())
-        rows = eng2.dets[:, :max(mx, 1)].cpu()
-        d2h = counts.numel() * 4 + rows.numel() * 4
-    e3.record()
+    pend = det.submit(hosts[0])
+    for i in range(1, args.steps + 1):
+        nxt = det.submit(hosts[i & 1]) if i < args.steps else None
+        det.collect(pend)
+        d2h = pend.d2h_bytes
+        pend = nxt
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3      # host clock: the region starts and ends on the host by definition
     barrier()
-    e2e_ms = e2.elapsed_time(e3)
+    # the reference's float32 tensor through the synchronous call (same pixels)
+    hosts_f32 = torch.from_numpy(synth.images_u8_to_f32(hosts[0].numpy())).pin_memory()
+    det.detect(hosts_f32)
+    barrier()
+    t0 = time.perf_counter()
+    nf = max(3, args.steps // 4)
+    for _ in range(nf):
+        det.detect(hosts_f32)
+    torch.cuda.synchronize()
+    e2e_f32_ms = (time.perf_counter() - t0) * 1e3 / nf
     sampler.stop_flag = True
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, e2e_f32_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, e2e_f32_ms = float(t[0]), float(t[1]), float(t[2])
 
     # ---------------------------------------------------------------- per-op eager pass (kernel-level roofline)
     table = []
     if rank == 0:
-        eng.run_network(); eng.run_decode(False, False, True); eng.run_nms(CONF, IOU)
+        x_u8 = eng.input_buffer("u8", 0)
+        eng.run_network(x_u8); eng.run_decode(False, False, True); eng.run_nms(CONF, IOU)
         torch.cuda.synchronize()
         import ctypes as C
         from transparent_object_detection_b200._lib import check
@@ -231,8 +243,8 @@ def main():
                     check(eng.L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
                 elif kind == "stem":
                     w, bb, out = payload
-                    check(eng.L.tod_stem_conv_nchw_f32(eng.x_static.data_ptr(), w.data_ptr(), bb.data_ptr(), out.ptr, B, args.size,
-                                                       args.size, C_, out.pitch, st), name)
+                    check(eng.L.tod_stem_conv_nhwc_u8(x_u8.data_ptr(), w.data_ptr(), bb.data_ptr(), out.ptr, B, args.size,
+                                                      args.size, C_, out.pitch, st), name)
                 else:
                     buf, c_ = payload
                     check(eng.L.tod_sppf_pool_nhwc_bf16(buf.ptr, B, buf.h, buf.w, c_, buf.pitch, st), name)
@@ -288,10 +300,13 @@ def main():
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"scale {args.scale} detector (BaseModel(80,{C_},{d},{m})), batch {B} per GPU, {args.size}x{args.size}, "
-                                       f"nc 80, conf {CONF} iou {IOU}, random-init weights",
+                                       f"nc 80, conf {CONF} iou {IOU}, random-init weights, uint8 NHWC images (/255 fused into the stem)",
                            "timing": "CUDA events around K graph replays; activations per pass (~2.5 GB) exceed L2 (126 MB)"},
-                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(hosts[0].numel() * 4), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_ms / args.steps},
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(hosts[0].numel()), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms / args.steps, "api": "Detector.submit/collect, 2 batches in flight, pinned uint8 host batch",
+                        "f32_input": {"value": B * world / (e2e_f32_ms / 1e3), "ms_per_step": e2e_f32_ms,
+                                      "h2d_bytes_per_step": int(hosts_f32.numel() * 4),
+                                      "api": "Detector.detect (synchronous) on the reference's float32 (B,3,H,W) tensor"}},
                 "gpu_launches": eng.launches_per_pass * args.steps,
                 "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
                 "breakdown_ms": {"conv": conv_ms, "stem": sum(r["ms"] for r in table if r["kind"] == "stem"),

@@ -95,6 +95,18 @@ int tod_stem_conv_nchw_f32(const float* d_x, const float* h_w, const float* h_bi
                            void* stream);
 
 /*
+ * Stem from uint8 images on the tensor cores, with the reference's pre-processing fused in: replaces
+ * `np.array(image, float32) / 255.0` + HWC->CHW (utils/callbacks.py:142-144, dataset/coco/get_map.py:52-60) followed by
+ * backbone.stem (model/backbone.py:20).  Pixel values are exact in bf16; 1/255 is folded into the bf16 weights.
+ *   d_x   u8 [batch, hin, win, 3] (device, the letterboxed RGB images)
+ *   h_w, h_bias  as for tod_stem_conv_nchw_f32 (HOST pointers, BN folded, K index = c*9 + kh*3 + kw)
+ *   d_out bf16 [batch, hin/2, win/2, out_pitch] (device)
+ */
+int tod_stem_conv_nhwc_u8(const uint8_t* d_x, const float* h_w, const float* h_bias, void* d_out,
+                          int32_t batch, int32_t hin, int32_t win, int32_t cout, int32_t out_pitch,
+                          void* stream);
+
+/*
  * SPPF pooling: three chained MaxPool2d(5, 1, 2) evaluated in shared memory.
  * Replaces SPPF.forward's pooling + torch.cat  model/blocks.py:139-141.
  * d_buf is the bf16 concat buffer [batch, h, w, pitch] whose channels [0, c) already hold cv1's output;

@@ -133,6 +133,17 @@ def make_images(batch: int, h: int, w: int, seed: int) -> np.ndarray:
     return r.random((batch, 3, h, w), dtype=np.float32)
 
 
+def make_images_u8(batch: int, h: int, w: int, seed: int) -> np.ndarray:
+    """uint8 NHWC (B, H, W, 3) letterboxed-image stand-ins; the reference's tensor for the same pixels is
+    `images_u8_to_f32` of it (np.array(image, float32) / 255.0, HWC -> CHW, utils/callbacks.py:142-144)."""
+    r = np.random.Generator(np.random.PCG64([seed, 0x08E5]))
+    return r.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)
+
+
+def images_u8_to_f32(u8: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(np.transpose(u8.astype(np.float32) / np.float32(255.0), (0, 3, 1, 2)))
+
+
 def make_dense_predictions(batch: int, anchors: int = 8400, nc: int = 80, objects: int = 120,
                            seed: int = 1234) -> np.ndarray:
     """clustered boxes, (B, A, 4+nc) float32 normalised xywh + scores."""

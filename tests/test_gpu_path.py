@@ -296,3 +296,58 @@ def test_detector_graph_matches_eager_and_oracle_nms():
     assert_dets_equal(got, want)
     assert_dets_equal(got2, want)
     assert any(w is not None for w in want)
+
+
+# ------------------------------------------------------------------------------------------ uint8 input path
+@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 32), (1, 32, 32, 16), (1, 640, 640, 32), (3, 38, 50, 64), (1, 64, 64, 128)])
+def test_stem_u8_tensor_core(B, H, W, cout):
+    """uint8 NHWC stem on tcgen05 == conv2d of (u8 / 255) with the SAME bf16-rounded (weights / 255): the only other
+    differences are fp32 accumulation order, the tanh-form SiLU (<= |x| * 2.5e-4) and bf16 output rounding."""
+    _lib, L = _engine_parts()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).cuda()
+    w = torch.randn((cout, 3, 3, 3), generator=g) * (2.0 / 27) ** 0.5
+    b = torch.randn((cout,), generator=g) * 0.3
+    out = torch.zeros((B, H // 2, W // 2, cout), dtype=torch.bfloat16).cuda()
+    wh = w.reshape(cout, 27).contiguous()
+    _lib.check(L.tod_stem_conv_nhwc_u8(u8.data_ptr(), wh.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, cout, cout,
+                                       torch.cuda.current_stream().cuda_stream), "stem_u8")
+    wq = (w * np.float32(1.0 / 255.0)).to(torch.bfloat16).float().cuda()
+    x = u8.permute(0, 3, 1, 2).float()
+    want = F.silu(F.conv2d(x, wq, b.cuda(), stride=2, padding=1)).permute(0, 2, 3, 1)
+    err = (out.float() - want).abs()
+    assert float((err - 1e-2 * want.abs()).max()) <= 1e-2, float(err.max())
+    # and against the fp32 reference arithmetic (x / 255 with unrounded weights): bf16-level agreement
+    ref = F.silu(F.conv2d(x / 255.0, w.cuda(), b.cuda(), stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert float(((out.float() - ref).abs() - 2e-2 * ref.abs()).max()) <= 2e-2
+
+
+def test_detector_uint8_pipeline_matches_float_path_and_is_order_safe():
+    """uint8 (B, H, W, 3) input == float32 (u8 / 255) input within the stated bf16 tolerance at the network output;
+    two batches submitted back to back (double-buffered upload) give exactly the rows of two synchronous calls."""
+    from oracle import synth
+    from transparent_object_detection_b200 import BaseModel, Detector
+    C_, d, m = synth.SCALES["n"]
+    model = BaseModel(80, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    g = torch.Generator().manual_seed(5)
+    u8a = torch.randint(0, 256, (3, 160, 192, 3), generator=g, dtype=torch.uint8)
+    u8b = torch.randint(0, 256, (3, 160, 192, 3), generator=g, dtype=torch.uint8)
+    det = Detector(model, (160, 192), confidence=0.01, nms_iou=0.5, letterbox_image=True)
+    ra, rb = det.detect(u8a.pin_memory()), det.detect(u8b.pin_memory())
+    pa = det.submit(u8a.pin_memory())
+    pb = det.submit(u8b.pin_memory())
+    assert_dets_equal(det.collect(pa), ra)
+    assert_dets_equal(det.collect(pb), rb)
+    assert any(r is not None for r in ra)
+    # network outputs of the two input formats agree to the bf16 tolerance
+    eng = model.engine(3, 160, 192)
+    eng.run_network(u8a.cuda()); eng.run_decode(True, False, False)
+    torch.cuda.synchronize()
+    o_u8 = eng.head_out.clone()
+    xf = (u8a.permute(0, 3, 1, 2).float() / 255.0).contiguous().cuda()
+    eng.run_network(xf); eng.run_decode(True, False, False)
+    torch.cuda.synchronize()
+    o_f = eng.head_out
+    assert float((o_u8[:, :4] - o_f[:, :4]).abs().max()) <= 1.5
+    assert float((o_u8[:, 4:] - o_f[:, 4:]).abs().max()) <= 8e-3

@@ -18,6 +18,7 @@ SOURCES = {
     "conv_tcgen05.cu": [],
     "conv_halo_tcgen05.cu": [],
     "stem_conv.cu": [],
+    "stem_u8_tcgen05.cu": [],
     "sppf_pool.cu": [],
     "head_decode.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],

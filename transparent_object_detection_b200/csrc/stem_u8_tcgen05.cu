@@ -1,0 +1,209 @@
+// Stem on the tensor cores from uint8 images: Conv2d(3, cout, 3, s2, p1) + folded BN + SiLU with the reference's
+// `/255` pre-processing fused in.   uint8 NHWC (B, H, W, 3) in  ->  NHWC bf16 (B, H/2, W/2, out_pitch) out.
+//
+// Replaces backbone.stem (model/backbone.py:20; Conv.forward model/blocks.py:52-54) together with the host-side
+// `np.array(image, float32) / 255.0` + HWC->CHW transpose in front of it (utils/callbacks.py:142-144,
+// dataset/coco/get_map.py:52-60).  The CUDA-core stem (stem_conv.cu, 864 FMAs per output pixel) is FP32-FMA bound; here
+// each 128-pixel tile builds its im2col rows (K = 27 padded to 32) in shared memory and two tcgen05 MMAs do the rest.
+// Pixel values 0..255 are exact in bf16 and the 1/255 scale is folded into the bf16 weights, so this path adds no
+// input quantisation on top of the weight rounding every other conv has.
+//
+// K index of a row = (kh * 3 + kw) * 3 + c  (9 contiguous bytes of an input row per kh); weights arrive as the folded
+// f32 [cout][c * 9 + kh * 3 + kw] HOST array of tod_stem_conv_nchw_f32 and are re-ordered / scaled / rounded here.
+#include <cstring>
+
+#include "tod_common.cuh"
+
+namespace tod {
+
+constexpr int kStemU8Threads = 128;   // one accumulator row (= output pixel) per thread
+
+template <int COUT>
+struct StemU8Weights {
+  float w[COUT * 27];   // [cout][c*9 + kh*3 + kw], BN folded
+  float b[COUT];
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kStemU8Threads) stem_u8_tcgen05_kernel(const uint8_t* __restrict__ x,
+                                                                        __nv_bfloat16* __restrict__ out, int hin, int win,
+                                                                        int out_pitch, long long total_pix,
+                                                                        long long num_tiles,
+                                                                        const __grid_constant__ StemU8Weights<COUT> wt) {
+  constexpr uint32_t kCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : 128);
+  __shared__ __align__(1024) uint8_t a_tile[128 * 64];      // 128 rows x 32 bf16, SWIZZLE_64B
+  __shared__ __align__(1024) uint8_t b_tile[COUT * 64];     // COUT rows x 32 bf16, SWIZZLE_64B
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int t = threadIdx.x, warp = t >> 5;
+  const int hout = hin >> 1, wout = win >> 1;
+  if (t == 0) {
+    mbar_init(&mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_smem, kCols);
+    tmem_relinquish();
+  }
+
+  // ---- B tile: weights / 255, bf16, row n at n*64 bytes, 16-byte chunk j stored at j ^ ((n >> 1) & 3)
+  for (int i = t; i < COUT * 16; i += kStemU8Threads) {     // one u32 (two K values) per iteration
+    const int n = i >> 4, kp = (i & 15) * 2;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = kp + e;
+      float wv = 0.f;
+      if (k < 27) {
+        const int tap = k / 3, c = k - tap * 3;
+        wv = wt.w[n * 27 + c * 9 + tap] * (1.0f / 255.0f);
+      }
+      v[e] = wv;
+    }
+    const uint32_t chunk = (kp >> 3) ^ ((n >> 1) & 3);
+    *reinterpret_cast<uint32_t*>(b_tile + n * 64 + chunk * 16 + (kp & 7) * 2) = pack_bf16x2(v[0], v[1]);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO = 8 rows x 64 B, SWIZZLE_64B
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(COUT >> 3) << 17) | ((128u >> 4) << 24);
+  uint32_t phase = 0;
+
+  // persistent loop: a handful of CTAs per SM interleave (im2col build | MMA | epilogue) of different tiles
+#pragma unroll 1
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, phase ^= 1u) {
+    // ---- A tile: this thread's im2col row
+    const long long pix = tile * 128 + t;
+    {
+      uint32_t words[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) words[i] = 0;
+      if (pix < total_pix) {
+        const int ipix = static_cast<int>(pix);          // < 2^31, checked on the host
+        const int r = ipix / wout;
+        const int ow = ipix - r * wout;
+        const int n = r / hout;
+        const int oh = r - n * hout;
+        const uint8_t* xn = x + static_cast<long long>(n) * hin * win * 3;
+        float v[28];
+        v[27] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int ih = 2 * oh + kh - 1;
+          const bool row_ok = ih >= 0 && ih < hin;
+          const uint8_t* xr = xn + (static_cast<long long>(ih) * win + (2 * ow - 1)) * 3;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            const int iw = 2 * ow - 1 + j / 3;
+            const bool ok = row_ok && iw >= 0 && iw < win;
+            v[kh * 9 + j] = ok ? static_cast<float>(__ldg(xr + j)) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 14; ++i) words[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t chunk = j ^ ((t >> 1) & 3);
+        *reinterpret_cast<uint4*>(a_tile + t * 64 + chunk * 16) =
+            make_uint4(words[4 * j], words[4 * j + 1], words[4 * j + 2], words[4 * j + 3]);
+      }
+    }
+    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();               // also: every thread has drained the previous tile's accumulator
+    tcgen05_fence_after();
+    if (warp == 0) {
+      if (elect_one()) {
+        umma_bf16_k2(tmem, umma_desc_lo(smem_u32(a_tile)), hi, umma_desc_lo(smem_u32(b_tile)), hi, idesc, 0u);
+        umma_commit(&mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&mma_bar, phase);    // MMAs complete: accumulator ready, a_tile free again
+    tcgen05_fence_after();
+
+    // ---- epilogue: thread t owns accumulator row t
+    __nv_bfloat16* o = out + pix * out_pitch;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(taddr + c0, v);
+      tmem_ld_wait();
+      if (pix < total_pix) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = silu_from_half(fmaf(__uint_as_float(v[j]), 0.5f, 0.5f * wt.b[c0 + j]));
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          uint4 ov;
+          ov.x = pack_bf16x2(f[j], f[j + 1]);
+          ov.y = pack_bf16x2(f[j + 2], f[j + 3]);
+          ov.z = pack_bf16x2(f[j + 4], f[j + 5]);
+          ov.w = pack_bf16x2(f[j + 6], f[j + 7]);
+          *reinterpret_cast<uint4*>(o + c0 + j) = ov;
+        }
+      }
+    }
+    tcgen05_fence_before();        // the next iteration's __syncthreads orders these TMEM reads before its MMA
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, kCols);
+  }
+}
+
+template <int COUT>
+static int launch_stem_u8(const uint8_t* d_x, const float* h_w, const float* h_bias, void* d_out, int batch, int hin, int win,
+                          int out_pitch, cudaStream_t st) {
+  StemU8Weights<COUT> wt;
+  memcpy(wt.w, h_w, sizeof(wt.w));
+  if (h_bias) memcpy(wt.b, h_bias, sizeof(wt.b)); else memset(wt.b, 0, sizeof(wt.b));
+  const long long total = static_cast<long long>(batch) * (hin / 2) * (win / 2);
+  const long long tiles = (total + 127) / 128;
+  TOD_CHECK_ARG(total < (1ll << 31), "stem_u8: too many output pixels");
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms = 148;
+  // CTAs per SM: bounded by TMEM (512 columns) and by what hides the build -> MMA -> epilogue latency chain
+  constexpr int kCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : 128);
+  const int per_sm = 512 / kCols < 8 ? 512 / kCols : 8;
+  long long blocks = static_cast<long long>(sms) * per_sm;
+  if (blocks > tiles) blocks = tiles;
+  stem_u8_tcgen05_kernel<COUT><<<static_cast<unsigned>(blocks), kStemU8Threads, 0, st>>>(
+      d_x, reinterpret_cast<__nv_bfloat16*>(d_out), hin, win, out_pitch, total, tiles, wt);
+  TOD_CHECK_LAUNCH("stem_u8_tcgen05_kernel launch");
+  return TOD_OK;
+}
+
+}  // namespace tod
+
+using namespace tod;
+
+extern "C" int tod_stem_conv_nhwc_u8(const uint8_t* d_x, const float* h_w, const float* h_bias, void* d_out, int32_t batch,
+                                     int32_t hin, int32_t win, int32_t cout, int32_t out_pitch, void* stream) {
+  TOD_CHECK_ARG(d_x && h_w && d_out, "stem_u8: null pointer");
+  TOD_CHECK_ARG(batch > 0 && hin > 0 && win > 0 && hin % 2 == 0 && win % 2 == 0, "stem_u8: bad shape %d x %d x %d", batch,
+                hin, win);
+  TOD_CHECK_ARG(out_pitch >= cout && out_pitch % 8 == 0, "stem_u8: out_pitch %d", out_pitch);
+  TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "stem_u8: output must be 16-byte aligned");
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (cout) {
+    case 16: return launch_stem_u8<16>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 32: return launch_stem_u8<32>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 48: return launch_stem_u8<48>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 64: return launch_stem_u8<64>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 96: return launch_stem_u8<96>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    case 128: return launch_stem_u8<128>(d_x, h_w, h_bias, d_out, batch, hin, win, out_pitch, st);
+    default:
+      set_error("stem_u8: unsupported cout %d (supported: 16, 32, 48, 64, 96, 128)", cout);
+      return TOD_ERR_UNSUPPORTED;
+  }
+}

@@ -107,6 +107,9 @@ class DetectorEngine:
         self.conv_meta: Dict[str, dict] = {}          # fp32 weights / views per conv (tools/gpu_netcheck.py)
         self.launches_forward = 0
         self._graph = None
+        self._graphs: Dict[Tuple, "torch.cuda.CUDAGraph"] = {}   # (input kind, slot, conf, iou, head_out, decoded)
+        self._inputs: Dict[Tuple[str, int], torch.Tensor] = {}   # static input buffers per (kind, slot)
+        self._slot_out: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._build(state_dict)
 
     # ------------------------------------------------------------------ memory
@@ -264,20 +267,43 @@ class DetectorEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def input_buffer(self, kind: str = "f32", slot: int = 0) -> torch.Tensor:
+        """Static device input of the captured graphs: kind "f32" = float32 NCHW in [0, 1] (the reference's tensor),
+        kind "u8" = uint8 NHWC letterboxed RGB (the /255 is fused into the stem).  Two slots allow the upload of batch
+        i+1 to overlap the graph replay of batch i."""
+        if kind == "f32" and slot == 0:
+            return self.x_static
+        key = (kind, slot)
+        if key not in self._inputs:
+            shape = (self.batch, 3, self.in_h, self.in_w) if kind == "f32" else (self.batch, self.in_h, self.in_w, 3)
+            self._inputs[key] = torch.zeros(shape, dtype=torch.float32 if kind == "f32" else torch.uint8, device=self.device)
+        return self._inputs[key]
+
+    def slot_outputs(self, slot: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-slot copies of (keep_count, dets): the graph's own result buffers are reused by the next replay."""
+        if slot not in self._slot_out:
+            self._slot_out[slot] = (torch.zeros_like(self.keep_count), torch.zeros_like(self.dets))
+        return self._slot_out[slot]
+
     def run_network(self, x: Optional[torch.Tensor] = None) -> None:
-        """Enqueue stem + every conv + SPPF pooling (the raw head maps land in self.raw)."""
+        """Enqueue stem + every conv + SPPF pooling (the raw head maps land in self.raw).
+        x: float32 (B, 3, H, W) in [0, 1]  or  uint8 (B, H, W, 3)."""
         st = self._stream()
         L = self.L
         if x is None:
             x = self.x_static
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == tuple(self.x_static.shape)
+        u8 = x.dtype == torch.uint8
+        want = (self.batch, self.in_h, self.in_w, 3) if u8 else tuple(self.x_static.shape)
+        assert x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous() and tuple(x.shape) == want, \
+            (x.dtype, tuple(x.shape), want)
         for kind, name, payload in self.ops:
             if kind == "conv":
                 check(L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
             elif kind == "stem":
                 w, b, out = payload
-                check(L.tod_stem_conv_nchw_f32(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.ptr, self.batch, self.in_h,
-                                               self.in_w, self.C, out.pitch, st), name)
+                fn = L.tod_stem_conv_nhwc_u8 if u8 else L.tod_stem_conv_nchw_f32
+                check(fn(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.ptr, self.batch, self.in_h, self.in_w, self.C,
+                         out.pitch, st), name)
             elif kind == "pool":
                 buf, c_ = payload
                 check(L.tod_sppf_pool_nhwc_bf16(buf.ptr, self.batch, buf.h, buf.w, c_, buf.pitch, st), name)
@@ -330,6 +356,35 @@ class DetectorEngine:
 
     def replay(self) -> None:
         self._graph.replay()
+
+    def graph_for(self, kind: str, slot: int, conf_thres: float, nms_thres: float):
+        """CUDA graph of network + decode + NMS (+ copy of the results into the slot's buffers) on the static input
+        (kind, slot); captured on first use."""
+        key = (kind, slot, float(conf_thres), float(nms_thres))
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        x = self.input_buffer(kind, slot)
+        cnt, dets = self.slot_outputs(slot)
+
+        def body():
+            self.run_network(x)
+            self.run_decode(False, False, True)
+            self.run_nms(conf_thres, nms_thres)
+            cnt.copy_(self.keep_count)
+            dets.copy_(self.dets)
+
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            body()           # warm-up outside capture (function attributes, module loading)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        self._graphs[key] = g
+        return g
 
     def raw_maps_nchw(self) -> List[torch.Tensor]:
         """Training-mode Head output layout (B, 64+nc, h, w) (model/head.py:50-51) as views of the raw maps."""

@@ -283,11 +283,70 @@ class Detector:
         return eng
 
     def detect(self, images: torch.Tensor, image_shape=None) -> List[Optional[np.ndarray]]:
-        """-> list of None | float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] like non_max_suppression."""
-        eng = self.detect_device(images)
-        counts = eng.keep_count.cpu().numpy()
+        """-> list of None | float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] like non_max_suppression.
+        images: float32 (B, 3, H, W) in [0, 1] (the reference's tensor) or uint8 (B, H, W, 3) letterboxed RGB."""
+        return self.collect(self.submit(images), image_shape)
+
+    # -- pipelined form: submit batch i+1 before collecting batch i and the upload overlaps the previous replay ---------
+    def submit(self, images: torch.Tensor) -> "PendingBatch":
+        """Enqueue upload (copy stream) -> graph replay (compute stream) of one batch and return at once."""
+        if images.dim() != 4 or images.dtype not in (torch.float32, torch.uint8):
+            raise ValueError("images must be float32 (B, 3, H, W) or uint8 (B, H, W, 3)")
+        kind = "u8" if images.dtype == torch.uint8 else "f32"
+        if (kind == "u8" and images.shape[3] != 3) or (kind == "f32" and images.shape[1] != 3):
+            raise ValueError(f"bad image batch shape {tuple(images.shape)} for dtype {images.dtype}")
+        dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        eng = self.model.engine(images.shape[0], self.input_shape[0], self.input_shape[1], dev)
+        with torch.cuda.device(eng.device):
+            if not hasattr(self, "_pipe"):
+                self._pipe = {}
+            st = self._pipe.get(id(eng))
+            if st is None:
+                st = {"copy": torch.cuda.Stream(eng.device), "compute": torch.cuda.Stream(eng.device), "next": 0,
+                      "free": [None, None]}
+                self._pipe[id(eng)] = st
+            slot = st["next"]
+            st["next"] = slot ^ 1
+            g = eng.graph_for(kind, slot, self.confidence, self.nms_iou)       # captured on first use
+            x = eng.input_buffer(kind, slot)
+            caller = torch.cuda.current_stream(eng.device)
+            with torch.cuda.stream(st["copy"]):
+                st["copy"].wait_stream(caller)                   # `images` may have been produced on the caller's stream
+                if st["free"][slot] is not None:
+                    st["copy"].wait_event(st["free"][slot])      # the previous replay that read this slot has finished
+                x.copy_(images, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(st["copy"])
+            with torch.cuda.stream(st["compute"]):
+                st["compute"].wait_event(copied)
+                g.replay()
+                done = torch.cuda.Event()
+                done.record(st["compute"])
+            st["free"][slot] = done
+        return PendingBatch(eng, slot, done)
+
+    def collect(self, pending: "PendingBatch", image_shape=None) -> List[Optional[np.ndarray]]:
+        """Wait for a submitted batch and return the reference's rows (D2H of the counts, then of the kept rows only)."""
+        eng = pending.engine
+        pending.done.synchronize()
+        cnt, dets = eng.slot_outputs(pending.slot)
+        counts = cnt.cpu().numpy()
         shape = image_shape if image_shape is not None else self.input_shape
-        return dets_to_reference_rows(eng.dets, counts, self.input_shape, shape, self.letterbox_image)
+        rows = dets_to_reference_rows(dets, counts, self.input_shape, shape, self.letterbox_image)
+        pending.d2h_bytes = counts.nbytes + int(counts.max() if len(counts) else 0) * counts.shape[0] * 24
+        return rows
+
+    def detect_image_rows(self, image) -> Optional[np.ndarray]:
+        """One PIL image / (H, W, 3) uint8 array -> the reference's (n, 6) rows or None.  Letterbox on the host (PIL
+        BICUBIC like utils/utils.py:16-30); the uint8 pixels go to the GPU as they are (/255 is fused into the stem)."""
+        from PIL import Image
+        if not isinstance(image, Image.Image):
+            image = Image.fromarray(np.asarray(image))
+        image_shape = np.array(np.shape(image)[0:2])
+        image = image if image.mode == "RGB" else image.convert("RGB")
+        image_data = _letterbox(image, (self.input_shape[1], self.input_shape[0]), self.letterbox_image)
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(image_data, dtype=np.uint8))[None])
+        return self.detect(x, image_shape)[0]
 
     def detect_image(self, image_id, image, results: list, clsid2catid) -> list:
         """reference mAP_FOCUS.detect_image (dataset/coco/get_map.py:37-96): `image` is a PIL image or an
@@ -310,6 +369,13 @@ class Detector:
                             "bbox": [float(left), float(top), float(right - left), float(bottom - top)],
                             "score": float(top_conf[i])})
         return results
+
+
+class PendingBatch:
+    """Handle of a batch submitted with Detector.submit."""
+
+    def __init__(self, engine: DetectorEngine, slot: int, done: "torch.cuda.Event"):
+        self.engine, self.slot, self.done, self.d2h_bytes = engine, slot, done, 0
 
 
 def _letterbox(image, size, letterbox_image):
