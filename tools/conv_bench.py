@@ -20,6 +20,7 @@ from transparent_object_detection_b200 import BaseModel         # noqa: E402
 from transparent_object_detection_b200._lib import ConvDesc, check   # noqa: E402
 
 VARIANTS = {
+    "auto": dict(variant=0),
     "v1": dict(variant=1),
     "halo": dict(variant=2),
     "halo_m1": dict(variant=2, m=1),

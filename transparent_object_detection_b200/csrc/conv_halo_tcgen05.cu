@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     uint32_t pha = 0, phb = 0;
     const uint32_t sub16 = p.sub_bytes >> 4;
     const uint32_t b_ring = smem_base + p.off_b;
-    const int gsz = p.num_taps == 9 ? 3 : 1;   // taps per synchronisation group
+    const int gsz_ring = p.num_taps == 9 ? 3 : 1;   // taps per synchronisation group while weight tiles stream in
     const bool ks4 = p.ksteps == 4;
     WaitClock wc(p.prof != nullptr && lane == 0);
     const long long role_t0 = wc.begin();
@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * acc_cols;
       const bool wait_b = !p.stationary || lt == 0;   // resident weights are only awaited on the first pass
+      // once the weights are resident and landed there is nothing to wait for between taps: one group per K chunk
+      const int gsz = wait_b ? gsz_ring : p.num_taps;
 #pragma unroll 1
       for (int c = 0; c < p.chunks; ++c) {
         const uint32_t a_base = smem_base + ai * p.a_slot_bytes;
@@ -395,28 +397,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           tcgen05_fence_after();
           // ... then gsz * m * ksteps MMAs back to back
           if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              if (j < gsz) {
-                const int t = t0 + j;
-                const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
-                const uint32_t hi_a = p.tap_hi_a[t];
-                const uint32_t b_lo = umma_desc_lo(b_ring + (slot0 + j) * p.b_slot_bytes);
-                const uint32_t accf = (c | t) != 0 ? 1u : 0u;
 #pragma unroll 1
-                for (int mt = 0; mt < m_cur; ++mt) {
-                  const uint32_t d_t = tmem_acc + mt * p.block_n;
-                  const uint32_t al = a_lo + mt * sub16;
-                  if (ks4) {
-                    umma_bf16_k4(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
-                  } else {
+            for (int j = 0; j < gsz; ++j) {
+              const int t = t0 + j;
+              const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
+              const uint32_t hi_a = p.tap_hi_a[t];
+              const uint32_t b_lo = umma_desc_lo(b_ring + (slot0 + j) * p.b_slot_bytes);
+              const uint32_t accf = (c | t) != 0 ? 1u : 0u;
 #pragma unroll 1
-                    for (int k = 0; k < p.ksteps; ++k)
-                      umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, p.hi_b, p.idesc, accf | (k != 0 ? 1u : 0u));
-                  }
+              for (int mt = 0; mt < m_cur; ++mt) {
+                const uint32_t d_t = tmem_acc + mt * p.block_n;
+                const uint32_t al = a_lo + mt * sub16;
+                if (ks4) {
+                  umma_bf16_k4(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
+                } else {
+#pragma unroll 1
+                  for (int k = 0; k < p.ksteps; ++k)
+                    umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, p.hi_b, p.idesc, accf | (k != 0 ? 1u : 0u));
                 }
-                if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
               }
+              if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
             }
             if (t0 + gsz >= p.num_taps) {
               umma_commit(&a_empty[ai]);

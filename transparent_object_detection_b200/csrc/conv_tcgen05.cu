@@ -386,8 +386,22 @@ extern "C" int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_
 extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   int rc = validate(d);
   if (rc != TOD_OK) return rc;
-  // reserved[0]: kernel variant -- 0 auto, 1 per-tap loads (this file), 2 halo patches (conv_halo_tcgen05.cu)
-  if (d->reserved[0] != 1) return conv_halo_launch(d, stream);
+  // reserved[0]: kernel variant -- 0 auto, 1 per-tap loads (this file), 2 halo patches (conv_halo_tcgen05.cu).
+  // Auto follows the per-layer measurements in profiles/r1_conv_bench_*.txt: the halo kernel (1 CTA/SM, patch reuse,
+  // resident weights, TMA-store epilogue) wins on large maps and on 1x1 convs; the per-tap kernel (2 CTAs/SM) still
+  // wins where 16x8 patches tile the map badly (<= 40x40), on stride 2 with > 32 input channels (four parity patches
+  // per chunk) and on the few tiny or upsample-add 1x1 layers.
+  int variant = d->reserved[0];
+  if (variant == 0) {
+    const int wout = d->win / d->stride;
+    const long long mtot = static_cast<long long>(d->batch) * (d->hin / d->stride) * wout;
+    bool halo;
+    if (d->ksize == 3 && d->stride == 2) halo = d->cin <= 32;
+    else if (d->ksize == 3) halo = wout >= 64 && !(d->d_residual != nullptr && d->cin <= 32);
+    else halo = !(d->d_upadd != nullptr || (mtot <= 32768 && d->cout <= 256));
+    variant = halo ? 2 : 1;
+  }
+  if (variant == 2) return conv_halo_launch(d, stream);
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

@@ -106,10 +106,12 @@ class DetectorEngine:
         self.conv_flops = 0
         self.conv_meta: Dict[str, dict] = {}          # fp32 weights / views per conv (tools/gpu_netcheck.py)
         self.launches_forward = 0
+        self.fork_head = True          # head towers as parallel graph branches (graph_for)
         self._graph = None
         self._graphs: Dict[Tuple, "torch.cuda.CUDAGraph"] = {}   # (input kind, slot, conf, iou, head_out, decoded)
         self._inputs: Dict[Tuple[str, int], torch.Tensor] = {}   # static input buffers per (kind, slot)
         self._slot_out: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._side_streams: Dict[Tuple[str, int], "torch.cuda.Stream"] = {}
         self._build(state_dict)
 
     # ------------------------------------------------------------------ memory
@@ -285,10 +287,13 @@ class DetectorEngine:
             self._slot_out[slot] = (torch.zeros_like(self.keep_count), torch.zeros_like(self.dets))
         return self._slot_out[slot]
 
-    def run_network(self, x: Optional[torch.Tensor] = None) -> None:
+    def run_network(self, x: Optional[torch.Tensor] = None, fork: bool = False) -> None:
         """Enqueue stem + every conv + SPPF pooling (the raw head maps land in self.raw).
-        x: float32 (B, 3, H, W) in [0, 1]  or  uint8 (B, H, W, 3)."""
-        st = self._stream()
+        x: float32 (B, 3, H, W) in [0, 1]  or  uint8 (B, H, W, 3).
+        fork: issue the six head towers (box / cls x three levels, mutually independent: model/head.py:24-44) on side
+        streams as soon as their input feature exists, so that they overlap the rest of the neck and one another
+        (used inside graph capture, where the forks become parallel graph branches)."""
+        main = torch.cuda.current_stream(self.device)
         L = self.L
         if x is None:
             x = self.x_static
@@ -296,7 +301,8 @@ class DetectorEngine:
         want = (self.batch, self.in_h, self.in_w, 3) if u8 else tuple(self.x_static.shape)
         assert x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous() and tuple(x.shape) == want, \
             (x.dtype, tuple(x.shape), want)
-        for kind, name, payload in self.ops:
+        def issue(kind, name, payload, stream):
+            st = stream.cuda_stream
             if kind == "conv":
                 check(L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
             elif kind == "stem":
@@ -309,6 +315,34 @@ class DetectorEngine:
                 check(L.tod_sppf_pool_nhwc_bf16(buf.ptr, self.batch, buf.h, buf.w, c_, buf.pitch, st), name)
             else:  # pragma: no cover
                 raise AssertionError(kind)
+
+        if not fork:
+            for kind, name, payload in self.ops:
+                issue(kind, name, payload, main)
+            return
+        feature_done = {"neck.h2.cv2": 0, "neck.h4.cv2": 1, "neck.h6.cv2": 2}     # last op of each head input
+        joins = []
+        for kind, name, payload in self.ops:
+            if name.startswith("head."):
+                continue
+            issue(kind, name, payload, main)
+            lvl = feature_done.get(name)
+            if lvl is None:
+                continue
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for tower in ("box", "cls"):
+                side = self._side_streams.setdefault((tower, lvl), torch.cuda.Stream(self.device))
+                side.wait_event(ready)
+                prefix = f"head.{tower}.{lvl}."
+                for k2, n2, p2 in self.ops:
+                    if n2.startswith(prefix):
+                        issue(k2, n2, p2, side)
+                done = torch.cuda.Event()
+                done.record(side)
+                joins.append(done)
+        for done in joins:
+            main.wait_event(done)
 
     def run_decode(self, head_out: bool = True, decoded: bool = False, candidates: bool = True) -> None:
         d = DecodeDesc()
@@ -368,7 +402,7 @@ class DetectorEngine:
         cnt, dets = self.slot_outputs(slot)
 
         def body():
-            self.run_network(x)
+            self.run_network(x, fork=self.fork_head)
             self.run_decode(False, False, True)
             self.run_nms(conf_thres, nms_thres)
             cnt.copy_(self.keep_count)
