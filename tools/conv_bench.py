@@ -27,6 +27,8 @@ VARIANTS = {
     "halo_m2": dict(variant=2, m=2),
     "halo_ring": dict(variant=2, no_station=1),
     "halo_sa2": dict(variant=2, stages=2),
+    "halo_noact": dict(variant=2, act=0),        # timing experiments only (results differ by construction)
+    "halo_nores": dict(variant=2, nores=1),
 }
 
 
@@ -37,6 +39,10 @@ def clone_desc(d: ConvDesc, **kw) -> ConvDesc:
     n.reserved[1] = kw.get("m", 0)
     n.reserved[2] = kw.get("no_station", 0)
     n.num_stages = kw.get("stages", 0)
+    if "act" in kw:
+        n.act = kw["act"]
+    if kw.get("nores"):
+        n.d_residual = None
     return n
 
 

@@ -92,51 +92,112 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t smem_addr, uint32_t hi) {
 
 __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t smask) { return off ^ (((off >> 7) & smask) << 4); }
 
-struct RowCtx {
-  const float* bias_s;              // shared, indexed by column within the N tile
-  const float* up_ptr;              // global f32 row (already offset to n0) or null
-  const __nv_bfloat16* res_ptr;     // global bf16 row (already offset to n0) or null
-  int act;
-};
+// ---- epilogue arithmetic.  The epilogue warps are issue/latency bound on the HBM-bound layers (ncu: ~220 SASS
+// instructions per 32 columns, IPC 0.2 per SM sub-partition), so the kernel is specialised on (activation, output type,
+// extra operand) and the per-element work is FFMA2 (packed f32x2) + one MUFU.TANH + half an F2FP.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 
-// 16 accumulator columns [col, col+16) of this thread's row -> activation applied, in f[].
-// With SiLU the bias in shared memory is pre-halved: h = acc / 2 + b / 2 is one FMA, silu = h + h * tanh(h).
-__device__ __forceinline__ void epilogue_math16(const RowCtx& rc, const uint32_t* v, int col, float (&f)[16]) {
-  const bool silu = rc.act == TOD_ACT_SILU;
-  const float sc = silu ? 0.5f : 1.0f;
+// Extra epilogue operand of one 32-column chunk of this thread's row, held in registers so that its global loads are
+// issued one chunk ahead of their use.  EXTRA 1: bf16 residual (added after the activation, 64 B = 4 x 16 B);
+// EXTRA 2: f32 upsample-add (added before it, 128 B = 8 x 16 B).
+template <int EXTRA>
+struct ExtraRegs {
+  uint4 q[EXTRA == 2 ? 8 : (EXTRA == 1 ? 4 : 1)];
+  __device__ __forceinline__ void load(const void* row_ptr, int col, int n) {   // n = 16 or 32 columns
+    if (EXTRA == 1) {
+      const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(row_ptr) + col);
 #pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(rc.bias_s + col + j);
-    f[j] = fmaf(__uint_as_float(v[j]), sc, b.x);
-    f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc, b.y);
-    f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc, b.z);
-    f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc, b.w);
-  }
-  if (rc.up_ptr) {
+      for (int i = 0; i < 4; ++i)
+        if (i * 8 < n) q[i] = __ldg(g + i);
+    } else if (EXTRA == 2) {
+      const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(row_ptr) + col);
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 u = __ldg(reinterpret_cast<const float4*>(rc.up_ptr + col + j));
-      f[j] = fmaf(u.x, sc, f[j]);
-      f[j + 1] = fmaf(u.y, sc, f[j + 1]);
-      f[j + 2] = fmaf(u.z, sc, f[j + 2]);
-      f[j + 3] = fmaf(u.w, sc, f[j + 3]);
+      for (int i = 0; i < 8; ++i)
+        if (i * 4 < n) q[i] = __ldg(g + i);
     }
   }
-  if (silu) {
+};
+
+// N (16 or 32) accumulator columns of this thread's row -> bias / upsample-add / SiLU / residual -> N output values
+// packed for the staging panel: bf16 pairs (N/2 words) or f32 (N words) in o[].  With SiLU the bias in shared memory is
+// pre-halved:  h = acc/2 + b/2 is one FMA and silu(x) = h + h * tanh(h).
+template <int N, bool SILU, bool OUT_F32, int EXTRA>
+__device__ __forceinline__ void epilogue_math(const uint32_t* v, const float* bias_col, const ExtraRegs<EXTRA>& ex, bool ex_valid,
+                                              uint32_t* o) {
+  const uint64_t sc2 = SILU ? pk2(0.5f, 0.5f) : pk2(1.0f, 1.0f);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = silu_from_half(f[j]);
-  }
-  if (rc.res_ptr) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 8) {
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rc.res_ptr + col + j));
-      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 rf = unpack_bf16x2(rw[t]);
-        f[j + 2 * t] += rf.x;
-        f[j + 2 * t + 1] += rf.y;
+  for (int j = 0; j < N; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_col + j);
+    uint64_t f0 = ffma2(pk2u(v[j], v[j + 1]), sc2, pk2(b.x, b.y));
+    uint64_t f1 = ffma2(pk2u(v[j + 2], v[j + 3]), sc2, pk2(b.z, b.w));
+    if (EXTRA == 2) {
+      const uint4 u = ex.q[j >> 2];
+      if (ex_valid) {
+        f0 = ffma2(pk2u(u.x, u.y), sc2, f0);
+        f1 = ffma2(pk2u(u.z, u.w), sc2, f1);
       }
+    }
+    if (SILU) {
+      float h0, h1, h2, h3, t0, t1, t2, t3;
+      upk2(f0, h0, h1);
+      upk2(f1, h2, h3);
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t2) : "f"(h2));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t3) : "f"(h3));
+      f0 = ffma2(f0, pk2(t0, t1), f0);
+      f1 = ffma2(f1, pk2(t2, t3), f1);
+    }
+    if (EXTRA == 1) {
+      const uint4 rq = ex.q[j >> 3];
+      const uint32_t r0 = (j & 4) ? rq.z : rq.x, r1 = (j & 4) ? rq.w : rq.y;
+      if (ex_valid) {   // bf16 -> f32 is a 16-bit shift / mask
+        f0 = fadd2(f0, pk2u(r0 << 16, r0 & 0xffff0000u));
+        f1 = fadd2(f1, pk2u(r1 << 16, r1 & 0xffff0000u));
+      }
+    }
+    float a0, a1, a2, a3;
+    upk2(f0, a0, a1);
+    upk2(f1, a2, a3);
+    if (OUT_F32) {
+      o[j] = __float_as_uint(a0);
+      o[j + 1] = __float_as_uint(a1);
+      o[j + 2] = __float_as_uint(a2);
+      o[j + 3] = __float_as_uint(a3);
+    } else {
+      o[j >> 1] = pack_bf16x2(a0, a1);
+      o[(j >> 1) + 1] = pack_bf16x2(a2, a3);
     }
   }
 }
@@ -183,32 +244,7 @@ __device__ __forceinline__ void wait_set(const uint32_t (&bars)[4], const uint32
   }
 }
 
-// 16 accumulator columns of this thread's row: bias / upsample-add / SiLU / residual, then the 16-byte chunks go to the
-// swizzled staging panel.  col = column inside the N tile, pcol = column inside the panel.
-__device__ __forceinline__ void epilogue_store16(const RowCtx& rc, const uint32_t (&v)[16], int col, int pcol, uint32_t stage,
-                                                 uint32_t row_off, uint32_t smask, int out_f32) {
-  float f[16];
-  epilogue_math16(rc, v, col, f);
-  if (out_f32) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t o = swz(row_off + (pcol * 4 + j * 16), smask);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + o), "f"(f[4 * j]), "f"(f[4 * j + 1]),
-                   "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                   : "memory");
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t o = swz(row_off + (pcol * 2 + j * 16), smask);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + o), "r"(pack_bf16x2(f[8 * j], f[8 * j + 1])),
-                   "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])), "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
-                   "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
-                   : "memory");
-    }
-  }
-}
-
+template <bool SILU, bool OUT_F32, int EXTRA>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
@@ -254,7 +290,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.block_n; i += kHaloThreads - 64)
-      bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) * (p.act == TOD_ACT_SILU ? 0.5f : 1.0f) : 0.0f;
+      bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) * (SILU ? 0.5f : 1.0f) : 0.0f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -445,6 +481,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
+    static_assert(!(OUT_F32 && EXTRA != 0), "extra operands are only combined with bf16 output");
+    constexpr int kPanelCols = OUT_F32 ? 32 : 64;      // a full staging panel row is 128 bytes
+    constexpr int kChunks = kPanelCols / 32;           // 32-column chunks per panel
+    constexpr int kWordsPerChunk = OUT_F32 ? 32 : 16;  // packed output words of one chunk
     const int group = (warp - 2) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // accumulator row = pixel within the sub-tile
@@ -453,9 +493,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const uint32_t bar_id = 1 + group;
     const int npanels = ceil_div(p.block_n, p.pc);
     const uint32_t row_off = static_cast<uint32_t>(r) * p.pb;
-    RowCtx rc;
-    rc.bias_s = bias_s;
-    rc.act = p.act;
+    const int sts_chunks = p.pb >> 4;       // 16-byte chunks per staging row (2, 4 or 8)
     WaitClock wc(p.prof != nullptr && leader);
     const long long role_t0 = wc.begin();
     uint32_t lt = 0;
@@ -472,66 +510,100 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       for (int mt = 0; mt < m_cur; ++mt) {
         const int s = s0 + mt;
         int c1, c2, c3;
-        long long pix;
-        bool valid;
-        int h = 0, w = 0, img = 0;
+        const void* ex_row = nullptr;       // this thread's row of the extra operand (null: row outside the tensor)
         if (p.patch_mode) {
-          img = p.fd_tiles_per_img.div(s);
+          const int img = p.fd_tiles_per_img.div(s);
           const int rem = s - img * p.tiles_per_img;
           const int ti = p.fd_tiles_w.div(rem);
           c1 = (rem - ti * p.tiles_w) * kPatchW;
           c2 = ti * kPatchH;
           c3 = img;
-          h = c2 + (r >> 3);
-          w = c1 + (r & 7);
-          valid = h < p.hout && w < p.wout;
-          pix = (static_cast<long long>(img) * p.hout + h) * p.wout + w;
+          if (EXTRA != 0) {
+            const int h = c2 + (r >> 3), w = c1 + (r & 7);
+            if (h < p.hout && w < p.wout) {
+              if (EXTRA == 1)
+                ex_row = p.residual + ((static_cast<long long>(img) * p.hout + h) * p.wout + w) * p.res_pitch + n0;
+              else
+                ex_row = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
+            }
+          }
         } else {
           c1 = s * 128;
           c2 = 0;
           c3 = 0;
-          pix = static_cast<long long>(s) * 128 + r;
-          valid = pix < p.mtot;
-          if (p.upadd != nullptr) {   // only the upsample-add needs (img, h, w) of a flat pixel index
-            const int ipix = static_cast<int>(pix);
-            img = p.fd_hw.div(ipix);
-            const int rem = ipix - img * (p.hout * p.wout);
-            h = p.fd_wout.div(rem);
-            w = rem - h * p.wout;
+          if (EXTRA != 0) {
+            const long long pix = static_cast<long long>(s) * 128 + r;
+            if (pix < p.mtot) {
+              if (EXTRA == 1) {
+                ex_row = p.residual + pix * p.res_pitch + n0;
+              } else {   // only the upsample-add needs (img, h, w) of a flat pixel index
+                const int ipix = static_cast<int>(pix);
+                const int img = p.fd_hw.div(ipix);
+                const int rem = ipix - img * (p.hout * p.wout);
+                const int h = p.fd_wout.div(rem);
+                const int w = rem - h * p.wout;
+                ex_row = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
+              }
+            }
           }
         }
-        rc.up_ptr = nullptr;
-        rc.res_ptr = nullptr;
-        if (valid) {
-          if (p.upadd)
-            rc.up_ptr = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
-          if (p.residual) rc.res_ptr = p.residual + pix * p.res_pitch + n0;
-        }
+        const bool ex_valid = ex_row != nullptr;
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
+        ExtraRegs<EXTRA> ex[kChunks];
+        bool ex0_ready = false;             // ex[0] already holds the first chunk of the coming panel
 #pragma unroll 1
         for (int pn = 0; pn < npanels; ++pn) {
           const int col0 = pn * p.pc;
           const int ncols = min(p.pc, p.block_n - col0);
-          // the previous panel's TMA store must have finished reading the staging buffer
-          tw = wc.begin();
-          if (leader) bulk_wait_read_all();
-          named_bar_sync(bar_id, 128);
-          wc.end(2, tw);
-#pragma unroll 1
-          for (int c16 = 0; c16 < ncols; c16 += 32) {
-            uint32_t v0[16], v1[16];
-            const bool two = c16 + 16 < ncols;
-            tmem_ld_32x32b_x16(taddr0 + col0 + c16, v0);
-            if (two) tmem_ld_32x32b_x16(taddr0 + col0 + c16 + 16, v1);
-            tmem_ld_wait();
-            epilogue_store16(rc, v0, col0 + c16, c16, stage, row_off, p.smask, p.out_f32);
-            if (two) epilogue_store16(rc, v1, col0 + c16 + 16, c16 + 16, stage, row_off, p.smask, p.out_f32);
+          if (EXTRA != 0 && ex_valid && !ex0_ready) ex[0].load(ex_row, col0, min(32, ncols));
+          ex0_ready = false;
+          uint32_t o[kChunks * kWordsPerChunk];
+#pragma unroll
+          for (int ch = 0; ch < kChunks; ++ch) {
+            const int cc = ch * 32;
+            if (cc < ncols) {               // warp-uniform
+              const bool full = ncols - cc >= 32;
+              uint32_t v[32];
+              if (full) {
+                tmem_ld_32x32b_x32(taddr0 + col0 + cc, v);
+              } else {
+                tmem_ld_32x32b_x16(taddr0 + col0 + cc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+              }
+              if (EXTRA != 0 && ex_valid) {   // issue the next chunk's extra-operand loads one chunk ahead of their use
+                if (ch + 1 < kChunks) {
+                  if (cc + 32 < ncols) ex[ch + 1].load(ex_row, col0 + cc + 32, min(32, ncols - cc - 32));
+                } else if (pn + 1 < npanels) {
+                  ex[0].load(ex_row, col0 + p.pc, min(32, p.block_n - col0 - p.pc));
+                  ex0_ready = true;
+                }
+              }
+              tmem_ld_wait();
+              if (full)
+                epilogue_math<32, SILU, OUT_F32, EXTRA>(v, bias_s + col0 + cc, ex[ch], ex_valid, &o[ch * kWordsPerChunk]);
+              else
+                epilogue_math<16, SILU, OUT_F32, EXTRA>(v, bias_s + col0 + cc, ex[ch], ex_valid, &o[ch * kWordsPerChunk]);
+            }
           }
           if (mt == m_cur - 1 && pn == npanels - 1) {
             // last TMEM read of this accumulator stage: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+          }
+          // the previous panel's TMA store must have finished reading the staging buffer
+          tw = wc.begin();
+          if (leader) bulk_wait_read_all();
+          named_bar_sync(bar_id, 128);
+          wc.end(2, tw);
+          const int nvalid16 = (ncols * (OUT_F32 ? 4 : 2)) >> 4;   // 16-byte chunks of this row that hold data
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < sts_chunks && j < nvalid16) {
+              const uint32_t off = swz(row_off + j * 16, p.smask);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + off), "r"(o[4 * j]), "r"(o[4 * j + 1]),
+                           "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                           : "memory");
+            }
           }
           fence_proxy_async_smem();
           tw = wc.begin();
@@ -813,14 +885,37 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   return TOD_OK;
 }
 
+// kernel variants: [0..2] bf16 out, no activation, extra 0/1/2; [3..5] bf16 out, SiLU, extra 0/1/2; [6] f32 out, no
+// activation; [7] f32 out, SiLU
+using HaloKernel = void (*)(HaloParams);
+constexpr int kHaloVariants = 8;
+static HaloKernel halo_kernel(int i) {
+  switch (i) {
+    case 0: return conv_halo_tcgen05<false, false, 0>;
+    case 1: return conv_halo_tcgen05<false, false, 1>;
+    case 2: return conv_halo_tcgen05<false, false, 2>;
+    case 3: return conv_halo_tcgen05<true, false, 0>;
+    case 4: return conv_halo_tcgen05<true, false, 1>;
+    case 5: return conv_halo_tcgen05<true, false, 2>;
+    case 6: return conv_halo_tcgen05<false, true, 0>;
+    default: return conv_halo_tcgen05<true, true, 0>;
+  }
+}
+
 int conv_halo_launch(const tod_conv_desc* d, void* stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit);
+    for (int i = 0; i < kHaloVariants && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit);
   });
   int rc;
   if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_halo_tcgen05)")) != TOD_OK) return rc;
+  const bool silu = d->act == TOD_ACT_SILU, f32 = d->out_dtype == TOD_OUT_F32;
+  const int extra = d->d_residual != nullptr ? 1 : (d->d_upadd != nullptr ? 2 : 0);
+  TOD_CHECK_ARG(!(d->d_residual != nullptr && d->d_upadd != nullptr), "conv: residual and upsample-add are mutually exclusive");
+  TOD_CHECK_ARG(!(f32 && extra != 0), "conv: residual / upsample-add need bf16 output");
+  const int kvar = f32 ? (silu ? 7 : 6) : ((silu ? 3 : 0) + extra);
 
   HaloParams p;
   size_t smem = 0;
@@ -837,7 +932,8 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream) {
   if (grid > work) grid = work;
   grid -= grid % p.n_tiles;
   if (grid < p.n_tiles) grid = p.n_tiles;
-  conv_halo_tcgen05<<<static_cast<unsigned>(grid), kHaloThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  HaloKernel kern = halo_kernel(kvar);
+  kern<<<static_cast<unsigned>(grid), kHaloThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   TOD_CHECK_LAUNCH("conv_halo_tcgen05 launch");
   return TOD_OK;
 }
