@@ -27,6 +27,9 @@ VARIANTS = {
     "halo_m2": dict(variant=2, m=2),
     "halo_ring": dict(variant=2, no_station=1),
     "halo_sa2": dict(variant=2, stages=2),
+    "halo_n128": dict(variant=2, ncap=128),
+    "halo_n128_m1": dict(variant=2, ncap=128, m=1),
+    "halo_n64": dict(variant=2, ncap=64),
     "halo_noact": dict(variant=2, act=0),        # timing experiments only (results differ by construction)
     "halo_nores": dict(variant=2, nores=1),
 }
@@ -38,6 +41,7 @@ def clone_desc(d: ConvDesc, **kw) -> ConvDesc:
     n.reserved[0] = kw.get("variant", 0)
     n.reserved[1] = kw.get("m", 0)
     n.reserved[2] = kw.get("no_station", 0)
+    n.reserved[3] = kw.get("ncap", 0)
     n.num_stages = kw.get("stages", 0)
     if "act" in kw:
         n.act = kw["act"]

@@ -41,6 +41,26 @@ struct FastDiv {
   __device__ __forceinline__ int div(int n) const { return static_cast<int>((static_cast<uint64_t>(n) * mul) >> 40); }
 };
 
+struct TileSched {
+  int full_rounds, G, g, m, tail_begin, tail_cnt;
+  __device__ __forceinline__ TileSched(int num_subtiles, int m_, int G_, int g_) : G(G_), g(g_), m(m_) {
+    full_rounds = num_subtiles / (G * m);
+    const int base = full_rounds * G * m, rem = num_subtiles - base;
+    tail_begin = base + static_cast<int>(static_cast<long long>(g) * rem / G);
+    tail_cnt = base + static_cast<int>(static_cast<long long>(g + 1) * rem / G) - tail_begin;
+  }
+  __device__ __forceinline__ int iters() const { return full_rounds + (tail_cnt > 0 ? 1 : 0); }
+  __device__ __forceinline__ void get(int it, int& s0, int& m_cur) const {
+    if (it < full_rounds) {
+      s0 = (it * G + g) * m;
+      m_cur = m;
+    } else {
+      s0 = tail_begin;
+      m_cur = tail_cnt;
+    }
+  }
+};
+
 struct __align__(64) HaloParams {
   CUtensorMap tm_a[4];
   CUtensorMap tm_w;
@@ -257,10 +277,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  // persistent schedule: this CTA owns N tile `nt` and super-tiles first, first + step, ...
+  // persistent schedule: this CTA owns N tile `nt`.  Full rounds are interleaved (CTA g takes super-tile r * G + g, so
+  // the grid streams through adjacent memory together); what is left after the last full round is split evenly at
+  // SUB-tile granularity, so the tail imbalance is one sub-tile instead of one super-tile of m.
   const int nt = blockIdx.x % p.n_tiles;
-  const int first = blockIdx.x / p.n_tiles;
-  const int step = gridDim.x / p.n_tiles;
+  const TileSched sched(p.num_subtiles, p.m, gridDim.x / p.n_tiles, blockIdx.x / p.n_tiles);
   const int n0 = nt * p.block_n;
   const int acc_cols = p.m * p.block_n;   // TMEM columns of one accumulator stage
   const uint32_t a_full0 = smem_u32(&a_full[0]), a_empty0 = smem_u32(&a_empty[0]);
@@ -314,10 +335,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       }
       int ai = 0, bi = 0;
       uint32_t pha = 0, phb = 0;   // ring phase bits
+      const int n_it = sched.iters();
 #pragma unroll 1
-      for (int st = first; st < p.num_super; st += step) {
-        const int s0 = st * p.m;
-        const int m_cur = min(p.m, p.num_subtiles - s0);
+      for (int it = 0; it < n_it; ++it) {
+        int s0, m_cur;
+        sched.get(it, s0, m_cur);
 #pragma unroll 1
         for (int c = 0; c < p.chunks; ++c) {
           long long tw = wc.begin();
@@ -380,14 +402,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const uint32_t sub16 = p.sub_bytes >> 4;
     const uint32_t b_ring = smem_base + p.off_b;
     const int gsz_ring = p.num_taps == 9 ? 3 : 1;   // taps per synchronisation group while weight tiles stream in
-    const bool ks4 = p.ksteps == 4;
+    const bool ks4 = p.ksteps == 4, ks2 = p.ksteps == 2;
     WaitClock wc(p.prof != nullptr && lane == 0);
     const long long role_t0 = wc.begin();
     const bool trace = wc.on && blockIdx.x == 0;   // CTA 0 also records a per-group timeline
     int ntrace = 0;
+    const int n_it = sched.iters();
 #pragma unroll 1
-    for (int st = first; st < p.num_super; st += step, ++lt) {
-      const int m_cur = min(p.m, p.num_subtiles - st * p.m);
+    for (int it = 0; it < n_it; ++it, ++lt) {
+      int s0, m_cur;
+      sched.get(it, s0, m_cur);
       const uint32_t acc = lt & 1;
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_empty_bar[acc]), ((lt >> 1) & 1) ^ 1u);
@@ -446,6 +470,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
                 const uint32_t al = a_lo + mt * sub16;
                 if (ks4) {
                   umma_bf16_k4(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
+                } else if (ks2) {   // 32-channel chunks: the rolled per-K loop below costs ~100 cycles per MMA in uniform-datapath latency
+                  umma_bf16_k2(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
                 } else {
 #pragma unroll 1
                   for (int k = 0; k < p.ksteps; ++k)
@@ -497,11 +523,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     WaitClock wc(p.prof != nullptr && leader);
     const long long role_t0 = wc.begin();
     uint32_t lt = 0;
+    const int n_it = sched.iters();
 #pragma unroll 1
-    for (int st = first; st < p.num_super; st += step, ++lt) {
+    for (int it = 0; it < n_it; ++it, ++lt) {
       if ((lt & 1) != static_cast<uint32_t>(group)) continue;
-      const int s0 = st * p.m;
-      const int m_cur = min(p.m, p.num_subtiles - s0);
+      int s0, m_cur;
+      sched.get(it, s0, m_cur);
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
       wc.end(1, tw);
@@ -662,7 +689,8 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.ksteps = bk >> 4;
   p.chunks = cin_pad / bk;
   p.num_taps = taps;
-  p.n_tiles = ceil_div(d->cout, 256);
+  const int n_cap = (d->reserved[3] >= 16 && d->reserved[3] <= 256) ? d->reserved[3] : 256;   // tools: cap on the N tile
+  p.n_tiles = ceil_div(d->cout, n_cap);
   p.block_n = round_up(ceil_div(d->cout, p.n_tiles), 16);
   p.b_tx_bytes = p.block_n * rb;
   p.b_slot_bytes = round_up(p.block_n * rb, 1024);

@@ -77,7 +77,7 @@ __device__ __forceinline__ void epilogue_store16(const ConvKernelParams& p, cons
   }
   if (p.act == TOD_ACT_SILU) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+    for (int j = 0; j < 16; ++j) f[j] = silu_from_half(0.5f * f[j]);   // one MUFU.TANH instead of EX2 + RCP
   }
   if (res_ptr) {
 #pragma unroll
@@ -388,17 +388,18 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   if (rc != TOD_OK) return rc;
   // reserved[0]: kernel variant -- 0 auto, 1 per-tap loads (this file), 2 halo patches (conv_halo_tcgen05.cu).
   // Auto follows the per-layer measurements in profiles/r1_conv_bench_*.txt: the halo kernel (1 CTA/SM, patch reuse,
-  // resident weights, TMA-store epilogue) wins on large maps and on 1x1 convs; the per-tap kernel (2 CTAs/SM) still
-  // wins where 16x8 patches tile the map badly (<= 40x40), on stride 2 with > 32 input channels (four parity patches
-  // per chunk) and on the few tiny or upsample-add 1x1 layers.
+  // resident weights, specialised TMA-store epilogue) wins on maps >= 40 wide and on almost every 1x1 conv; the per-tap
+  // kernel (2 CTAs/SM) still wins where 16x8 patches tile the map badly (20x20), on stride 2 with > 32 input channels
+  // (four parity patches per chunk), on wide-K / narrow-N 3x3 layers (cin >= 128 into <= 64 channels, or cin > 128 on a
+  // 40-wide map) and on the tiny 1x1 head outputs.
   int variant = d->reserved[0];
   if (variant == 0) {
     const int wout = d->win / d->stride;
     const long long mtot = static_cast<long long>(d->batch) * (d->hin / d->stride) * wout;
     bool halo;
     if (d->ksize == 3 && d->stride == 2) halo = d->cin <= 32;
-    else if (d->ksize == 3) halo = wout >= 64 && !(d->d_residual != nullptr && d->cin <= 32);
-    else halo = !(d->d_upadd != nullptr || (mtot <= 32768 && d->cout <= 256));
+    else if (d->ksize == 3) halo = wout >= 40 && !(d->cin >= 128 && d->cout <= 64) && !(wout < 64 && d->cin > 128);
+    else halo = !(mtot <= 32768 && d->cout <= 128);
     variant = halo ? 2 : 1;
   }
   if (variant == 2) return conv_halo_launch(d, stream);
