@@ -11,7 +11,7 @@
 namespace tod {
 
 constexpr int kDecThreads = 256;
-constexpr int kDecAnchors = 64;  // anchors per CTA (4 threads per anchor in the DFL phase)
+constexpr int kDecAnchors = 64;  // anchors per CTA (4 threads per anchor)
 
 struct DecodeParams {
   const float* raw[3];
@@ -28,10 +28,25 @@ struct DecodeParams {
   int* cand_cls;
 };
 
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }   // Tensor.sigmoid(), head.py:61
+
+// (score, class) candidates are ordered by score descending, then class ascending (torch.max keeps the first maximum)
+__device__ __forceinline__ void better(float& s, int& c, float s2, int c2) {
+  if (s2 > s || (s2 == s && c2 < c)) { s = s2; c = c2; }
+}
+
+// Four threads per anchor row (64 + nc f32 logits), 64 anchors per CTA.  Thread (a, j): DFL of box side j (16 bins,
+// 64 contiguous bytes) and a contiguous quarter of the class logits, so the four threads of an anchor read one
+// contiguous run.  FULL: every class score is materialised (Head tensor / decode_box tensor requested).  Otherwise only
+// the NMS candidate is needed: the class maximum is found on the LOGITS (each thread keeps its two largest) and the
+// sigmoid is evaluated only for logits within a window of the maximum wide enough to contain every float32 tie of the
+// scores (the reference takes max over the sigmoid outputs and keeps the lowest class among equal scores); where the
+// sigmoid saturates the window is everything.  Both modes produce bit-identical candidates.
+template <bool FULL>
 __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodeParams p) {
   extern __shared__ float dec_smem[];
   const int spitch = p.nc + 1;
-  float* s_score = dec_smem;                           // [64][nc + 1]
+  float* s_score = dec_smem;                           // [64][nc + 1]     (FULL only)
   float* s_box = dec_smem + kDecAnchors * spitch;      // [64][4]  xywh in input pixels
 
   int lvl = 0, tile = blockIdx.x;
@@ -44,57 +59,133 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
   const int na = min(kDecAnchors, la - a0);
   const float* raw = p.raw[lvl] + (static_cast<size_t>(b) * la + a0) * p.raw_pitch;
   const float stride = p.stride[lvl];
+  const unsigned full = 0xffffffffu;
+  const int ag0 = p.level_off[lvl] + a0;    // global anchor index of the CTA's first anchor
+  const float ninf = -INFINITY;
 
-  // ---- phase A: DFL, 4 threads per anchor (one per box side)
-  {
-    const int a = threadIdx.x >> 2, side = threadIdx.x & 3;
-    float dist = 0.f;
-    if (a < na) {
-      const float4* src = reinterpret_cast<const float4*>(raw + static_cast<size_t>(a) * p.raw_pitch + side * 16);
-      float l[16];
+  const int a = threadIdx.x >> 2, side = threadIdx.x & 3;
+  const bool valid = a < na;
+  const float4* row = reinterpret_cast<const float4*>(raw + static_cast<size_t>(valid ? a : 0) * p.raw_pitch);
+  // class chunks (4 classes each) of this thread: [k0, k1) of the ceil(nc / 4) chunks after the 16 box chunks
+  const int kc = (p.nc + 3) >> 2, per = (kc + 3) >> 2;
+  const int k0 = min(side * per, kc), k1 = min(k0 + per, kc);
+
+  // ---- DFL (blocks.py:154-157): softmax over the 16 bins of this side, expectation with arange(16)
+  float dist = 0.f;
+  if (valid) {
+    float l[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(src + i);
-        l[4 * i] = v.x; l[4 * i + 1] = v.y; l[4 * i + 2] = v.z; l[4 * i + 3] = v.w;
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(row + side * 4 + i);
+      l[4 * i] = v.x; l[4 * i + 1] = v.y; l[4 * i + 2] = v.z; l[4 * i + 3] = v.w;
+    }
+    float m = l[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, l[i]);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { l[i] = expf(l[i] - m); sum += l[i]; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dist += static_cast<float>(i) * (l[i] / sum);   // softmax, then arange(16) projection
+  }
+  // ---- classes
+  float best = -1.0f;
+  int bi = 0x7fffffff;
+  if (FULL) {
+    if (valid)
+      for (int k = k0; k < k1; ++k) {
+        const float4 v = __ldg(row + 16 + k);
+        const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * k + e;
+          if (c < p.nc) {
+            const float sc = sigmoid_ref(xs[e]);
+            s_score[a * spitch + c] = sc;
+            better(best, bi, sc, c);
+          }
+        }
       }
-      float m = l[0];
+  } else {
+    // the two largest logits of this thread (first occurrence wins ties, like the ascending-class scan of the scores)
+    float x1 = ninf, x2 = ninf;
+    int c1 = 0x7fffffff;
+    if (valid)
+      for (int k = k0; k < k1; ++k) {
+        const float4 v = __ldg(row + 16 + k);
+        const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 1; i < 16; ++i) m = fmaxf(m, l[i]);
-      float s = 0.f;
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * k + e;
+          if (c < p.nc) {
+            const float x = xs[e];
+            if (x > x1) { x2 = x1; x1 = x; c1 = c; }
+            else x2 = fmaxf(x2, x);
+          }
+        }
+      }
+    float m = x1;
+    m = fmaxf(m, __shfl_xor_sync(full, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(full, m, 2));
+    // float32 scores of two logits can only tie when the logits are this close (d sigmoid / dx = s (1 - s));
+    // outside (-80, 15) the sigmoid saturates and every class is evaluated
+    const float thr_logit = (m > -80.0f && m < 15.0f) ? m - (m > 8.0f ? 2.0f : 0.01f) : ninf;
+    if (valid) {
+      if (x2 >= thr_logit) {                 // rare: more than one of this thread's logits in the window -> rescan
+        for (int k = k0; k < k1; ++k) {
+          const float4 v = __ldg(row + 16 + k);
+          const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { l[i] = expf(l[i] - m); s += l[i]; }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) dist += static_cast<float>(i) * (l[i] / s);   // softmax, then arange(16) projection
-    }
-    // gather the four sides on the side-0 lane
-    const unsigned full = 0xffffffffu;
-    const int base = (threadIdx.x & 31) & ~3;
-    const float dl = __shfl_sync(full, dist, base + 0);
-    const float dt = __shfl_sync(full, dist, base + 1);
-    const float dr = __shfl_sync(full, dist, base + 2);
-    const float db = __shfl_sync(full, dist, base + 3);
-    if (side == 0 && a < na) {
-      const int ai = a0 + a;
-      const int gy = ai / lw, gx = ai - gy * lw;
-      const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;  // make_anchors
-      const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;                 // head.py:57-58
-      s_box[a * 4 + 0] = ((x1 + x2) / 2.0f) * stride;                                      // head.py:59-61
-      s_box[a * 4 + 1] = ((y1 + y2) / 2.0f) * stride;
-      s_box[a * 4 + 2] = (x2 - x1) * stride;
-      s_box[a * 4 + 3] = (y2 - y1) * stride;
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * k + e;
+            if (c < p.nc && xs[e] >= thr_logit) better(best, bi, sigmoid_ref(xs[e]), c);
+          }
+        }
+      } else if (x1 >= thr_logit) {
+        best = sigmoid_ref(x1);
+        bi = c1;
+      }
     }
   }
-  // ---- phase B: class sigmoid, coalesced over (anchor, class)
-  for (int i = threadIdx.x; i < na * p.nc; i += kDecThreads) {
-    const int a = i / p.nc, c = i - a * p.nc;
-    const float x = __ldg(raw + static_cast<size_t>(a) * p.raw_pitch + 64 + c);
-    s_score[a * spitch + c] = 1.0f / (1.0f + expf(-x));
+  // ---- combine the four threads of the anchor (lanes 4q .. 4q+3)
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const float s2 = __shfl_xor_sync(full, best, o);
+    const int c2 = __shfl_xor_sync(full, bi, o);
+    better(best, bi, s2, c2);
   }
+  const int base = (threadIdx.x & 31) & ~3;
+  const float dl = __shfl_sync(full, dist, base + 0);
+  const float dt = __shfl_sync(full, dist, base + 1);
+  const float dr = __shfl_sync(full, dist, base + 2);
+  const float db = __shfl_sync(full, dist, base + 3);
+  if (side == 0 && valid) {
+    const int ai = a0 + a;
+    const int gy = ai / lw, gx = ai - gy * lw;
+    const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;  // make_anchors
+    const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;                 // head.py:57-58
+    const float bx = ((x1 + x2) / 2.0f) * stride, by = ((y1 + y2) / 2.0f) * stride;     // head.py:59-61
+    const float bw = (x2 - x1) * stride, bh = (y2 - y1) * stride;
+    if (FULL) {
+      s_box[a * 4 + 0] = bx;
+      s_box[a * 4 + 1] = by;
+      s_box[a * 4 + 2] = bw;
+      s_box[a * 4 + 3] = bh;
+    }
+    // NMS candidate: corners of the normalised xywh (bbox_utils.py:144-148), class max (:153)
+    if (p.cand_conf) {
+      const size_t g = static_cast<size_t>(b) * p.anchors + ag0 + a;
+      p.cand_conf[g] = best;
+      p.cand_cls[g] = bi;
+      const float nx = bx / p.in_w, ny = by / p.in_h, nw = bw / p.in_w, nh = bh / p.in_h;
+      reinterpret_cast<float4*>(p.cand_box)[g] = make_float4(nx - nw / 2.0f, ny - nh / 2.0f, nx + nw / 2.0f, ny + nh / 2.0f);
+    }
+  }
+  if (!FULL) return;
   __syncthreads();
 
   const int no = 4 + p.nc;
-  const int ag0 = p.level_off[lvl] + a0;  // global anchor index of the CTA's first anchor
-  // ---- phase C1: Head eval tensor (B, 4+nc, A): contiguous along anchors
+  // ---- Head eval tensor (B, 4+nc, A): contiguous along anchors
   if (p.head_out) {
     float* o = p.head_out + static_cast<size_t>(b) * no * p.anchors + ag0;
     for (int i = threadIdx.x; i < no * kDecAnchors; i += kDecThreads) {
@@ -102,7 +193,7 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
       if (a < na) o[static_cast<size_t>(ch) * p.anchors + a] = ch < 4 ? s_box[a * 4 + ch] : s_score[a * spitch + ch - 4];
     }
   }
-  // ---- phase C2: decode_box tensor (B, A, 4+nc): contiguous rows, xywh / (W,H,W,H)
+  // ---- decode_box tensor (B, A, 4+nc): contiguous rows, xywh / (W,H,W,H)
   if (p.decoded) {
     float* o = p.decoded + (static_cast<size_t>(b) * p.anchors + ag0) * no;
     for (int i = threadIdx.x; i < na * no; i += kDecThreads) {
@@ -112,22 +203,6 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
       else v = s_score[a * spitch + ch - 4];
       o[i] = v;
     }
-  }
-  // ---- phase C3: NMS candidates: corners of the normalised xywh (bbox_utils.py:144-148), class max (:153)
-  if (p.cand_conf && threadIdx.x < na) {
-    const int a = threadIdx.x;
-    float best = s_score[a * spitch];
-    int bi = 0;
-    for (int c = 1; c < p.nc; ++c) {
-      const float v = s_score[a * spitch + c];
-      if (v > best) { best = v; bi = c; }   // strict: first (lowest) class wins ties, like torch.max on CPU
-    }
-    const size_t g = static_cast<size_t>(b) * p.anchors + ag0 + a;
-    p.cand_conf[g] = best;
-    p.cand_cls[g] = bi;
-    const float nx = s_box[a * 4 + 0] / p.in_w, ny = s_box[a * 4 + 1] / p.in_h;
-    const float nw = s_box[a * 4 + 2] / p.in_w, nh = s_box[a * 4 + 3] / p.in_h;
-    reinterpret_cast<float4*>(p.cand_box)[g] = make_float4(nx - nw / 2.0f, ny - nh / 2.0f, nx + nw / 2.0f, ny + nh / 2.0f);
   }
 }
 
@@ -195,17 +270,21 @@ extern "C" int tod_head_decode(const tod_decode_desc* d, void* stream) {
   p.cand_box = d->d_cand_box;
   p.cand_conf = d->d_cand_conf;
   p.cand_cls = d->d_cand_cls;
-  const size_t smem = (static_cast<size_t>(kDecAnchors) * (d->nc + 1) + kDecAnchors * 4) * sizeof(float);
+  const bool full_out = d->d_head_out != nullptr || d->d_decoded != nullptr;
+  const size_t smem = full_out ? (static_cast<size_t>(kDecAnchors) * (d->nc + 1) + kDecAnchors * 4) * sizeof(float) : 0;
   static bool attr_done = false;
   if (!attr_done) {
-    int rc = check_cuda(cudaFuncSetAttribute(head_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+    int rc = check_cuda(cudaFuncSetAttribute(head_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                         "cudaFuncSetAttribute(head_decode)");
     if (rc != TOD_OK) return rc;
     attr_done = true;
   }
   TOD_CHECK_ARG(smem <= 200 * 1024, "decode: nc %d too large for shared memory", d->nc);
   dim3 grid(total_tiles, d->batch, 1);
-  head_decode_kernel<<<grid, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (full_out)
+    head_decode_kernel<true><<<grid, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    head_decode_kernel<false><<<grid, kDecThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   TOD_CHECK_LAUNCH("head_decode_kernel launch");
   return TOD_OK;
 }

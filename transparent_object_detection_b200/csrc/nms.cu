@@ -20,8 +20,8 @@ namespace tod {
 
 constexpr int kSortThreads = 1024;
 constexpr int kSortSmemKeys = 16384;  // 128 KB of 64-bit keys
-constexpr int kSegWarps = 8;
-constexpr int kSegCtasPerImage = 32;
+constexpr int kSegWarps = 16;
+constexpr int kSegCtasPerImage = 16;
 constexpr int kIdxBits = 20, kScoreBits = 32;  // key = cls[12] | ~score[32] | idx[20]
 constexpr unsigned long long kIdxMask = (1ull << kIdxBits) - 1;
 
@@ -183,20 +183,162 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
   const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
   const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
   const float inter = w * h;
+  // disjoint boxes: inter == 0 -> iou is 0 (or NaN for two empty boxes), never > a non-negative threshold.  Skipping
+  // the IEEE division for them leaves every comparison result unchanged.
+  if (inter == 0.0f && thr >= 0.0f) return false;
   const float ovr = inter / (area_a + area_b - inter);
   return ovr > thr;
 }
 
-// One CTA per (image, class) segment.  Greedy NMS processes boxes in score order; a box's fate is known once it has
-// been compared with every EARLIER KEPT box.  Each round, warp 0 gathers the next <= 32 boxes that are still alive
-// (dead ones are skipped for good), resolves them among themselves (per-lane 32-bit IoU masks + a shuffle scan) and
-// publishes the kept ones; then the whole CTA sweeps the not-yet-visited tail of the segment against those kept boxes.
+// Greedy NMS of one class segment processes boxes in score order; a box's fate is known once it has been compared with
+// every EARLIER KEPT box.
+//
+// Segments of up to kWarpSegMax boxes (the common case: ~80 classes share a few thousand candidates) are handled by ONE
+// WARP each, 32 boxes at a time: a tile is first swept against the kept boxes of earlier tiles (a per-warp list in
+// shared memory), then resolved within itself (per-lane 32-bit IoU masks + a shuffle scan).  No block barriers and no
+// flag re-reads: many independent warps hide one another's load latency.
+// Larger segments fall back to the CTA-cooperative rounds below: warp 0 gathers the next <= 32 boxes that are still
+// alive (dead ones are skipped for good), resolves them among themselves and publishes the kept ones; then the whole
+// CTA sweeps the not-yet-visited tail of the segment against those kept boxes.
 // Work is O(kept x segment) instead of O(segment^2); the result is exactly the sequential greedy one.
+constexpr int kWarpSegMax = 128;     // boxes per warp-handled segment
+constexpr int kCtaSegSmem = 2048;     // boxes of a CTA-handled segment staged in shared memory (32 KB + flags)
+
+__device__ __forceinline__ void nms_warp_segment(const float4* __restrict__ boxes, const int* __restrict__ ord,
+                                                 unsigned char* __restrict__ flags, int len, float iou_thr, float4* kept_list,
+                                                 int lane) {
+  const unsigned full = 0xffffffffu;
+  int nk = 0;
+  for (int t0 = 0; t0 < len; t0 += 32) {
+    const int p = t0 + lane;
+    const bool has = p < len;
+    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has) bi = boxes[ord[p]];
+    const float area_i = (bi.z - bi.x) * (bi.w - bi.y);
+    bool alive = has;
+    for (int j = 0; j < nk && alive; ++j) {          // kept boxes of earlier tiles
+      const float4 bj = kept_list[j];
+      if (iou_gt(bj, (bj.z - bj.x) * (bj.w - bj.y), bi, area_i, iou_thr)) alive = false;
+    }
+    unsigned alive_bits = __ballot_sync(full, alive);
+    const int cnt = min(32, len - t0);
+    unsigned mask = 0;                                // later in-tile boxes this box suppresses
+    for (int j = 1; j < cnt; ++j) {
+      float4 bj;
+      bj.x = __shfl_sync(full, bi.x, j);
+      bj.y = __shfl_sync(full, bi.y, j);
+      bj.z = __shfl_sync(full, bi.z, j);
+      bj.w = __shfl_sync(full, bi.w, j);
+      const float area_j = __shfl_sync(full, area_i, j);
+      if (j > lane && iou_gt(bi, area_i, bj, area_j, iou_thr)) mask |= 1u << j;
+    }
+    for (int j = 0; j < cnt; ++j) {
+      const unsigned mj = __shfl_sync(full, mask, j);
+      if ((alive_bits >> j) & 1u) alive_bits &= ~mj;
+    }
+    const bool kept = has && ((alive_bits >> lane) & 1u);
+    if (has) flags[p] = kept ? 2 : 1;
+    if (t0 + 32 < len) {                              // only later tiles read the list
+      if (kept) kept_list[nk + __popc(alive_bits & ((1u << lane) - 1u))] = bi;
+      nk += __popc(alive_bits);
+      __syncwarp();
+    }
+  }
+}
+
+// One segment, whole CTA.  SMEM: boxes / flags are the staged shared-memory copies (index = position in the segment);
+// otherwise boxes are gathered through ord[] and the flags live in global memory.  flags: bit0 = suppressed, bit1 = kept.
+template <bool SMEM>
+__device__ __forceinline__ void nms_cta_segment(const float4* boxes, const int* ord, unsigned char* flags, int len, float iou_thr,
+                                                float4* s_kept, int* s_tilepos, int* s_ctl) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  auto box_at = [&](int k) { return SMEM ? boxes[k] : boxes[ord[k]]; };
+  if (threadIdx.x == 0) s_ctl[0] = 0;
+  __syncthreads();
+  while (true) {
+    if (warp == 0) {
+      // ---- gather the next <= 32 alive boxes in score order
+      int pos = s_ctl[0], cnt = 0;
+      while (cnt < 32 && pos < len) {
+        const int pp = pos + lane;
+        const bool al = pp < len && (flags[pp] & 1) == 0;
+        const unsigned bal = __ballot_sync(full, al);
+        const int avail = __popc(bal);
+        const int take = min(avail, 32 - cnt);
+        const int rank = __popc(bal & ((1u << lane) - 1u));
+        if (al && rank < take) s_tilepos[cnt + rank] = pp;
+        if (take < avail) {
+          const unsigned last = __ballot_sync(full, al && rank == take - 1);
+          pos += __ffs(last);          // one past the last box taken
+        } else {
+          pos += 32;
+        }
+        cnt += take;
+      }
+      __syncwarp();
+      // ---- resolve the tile: lane i owns the i-th gathered box (all are alive on entry)
+      const bool has = lane < cnt;
+      float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+      int my = 0;
+      if (has) {
+        my = s_tilepos[lane];
+        bi = box_at(my);
+      }
+      const float area_i = (bi.z - bi.x) * (bi.w - bi.y);
+      unsigned mask = 0;   // later in-tile boxes this box suppresses
+      for (int j = 1; j < cnt; ++j) {
+        float4 bj;
+        bj.x = __shfl_sync(full, bi.x, j);
+        bj.y = __shfl_sync(full, bi.y, j);
+        bj.z = __shfl_sync(full, bi.z, j);
+        bj.w = __shfl_sync(full, bi.w, j);
+        const float area_j = __shfl_sync(full, area_i, j);
+        if (j > lane && iou_gt(bi, area_i, bj, area_j, iou_thr)) mask |= 1u << j;
+      }
+      unsigned alive_bits = cnt >= 32 ? full : ((1u << cnt) - 1u);
+      for (int j = 0; j < cnt; ++j) {
+        const unsigned mj = __shfl_sync(full, mask, j);
+        if ((alive_bits >> j) & 1u) alive_bits &= ~mj;
+      }
+      const bool kept = has && ((alive_bits >> lane) & 1u);
+      if (has) flags[my] |= kept ? 2 : 1;
+      if (kept) s_kept[__popc(alive_bits & ((1u << lane) - 1u))] = bi;
+      if (lane == 0) {
+        s_ctl[0] = pos < len ? pos : len;
+        s_ctl[1] = cnt;
+        s_ctl[2] = __popc(alive_bits);
+      }
+    }
+    __syncthreads();
+    const int cnt = s_ctl[1], nk = s_ctl[2], pos = s_ctl[0];
+    if (cnt == 0) break;
+    // ---- kept boxes of this round suppress the unvisited tail
+    for (int k = pos + threadIdx.x; k < len; k += kSegWarps * 32) {
+      if (flags[k] & 1) continue;
+      const float4 bk = box_at(k);
+      const float area_k = (bk.z - bk.x) * (bk.w - bk.y);
+      for (int j = 0; j < nk; ++j) {
+        const float4 bj = s_kept[j];
+        if (iou_gt(bj, (bj.z - bj.x) * (bj.w - bj.y), bk, area_k, iou_thr)) {
+          flags[k] |= 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kSegWarps * 32) nms_segment_kernel(const float4* __restrict__ cand_box, int anchors,
                                                                      float iou_thr, NmsWork wk) {
+  // pass 1 uses the union as per-warp kept lists [kSegWarps][kWarpSegMax], pass 2 as staged boxes + flags of one segment
+  __shared__ __align__(16) unsigned char s_union[kCtaSegSmem * (sizeof(float4) + 1)];
   __shared__ float4 s_kept[32];
   __shared__ int s_tilepos[32];
-  __shared__ int s_pos, s_cnt, s_nk;
+  __shared__ int s_ctl[4];
+  static_assert(kSegWarps * kWarpSegMax <= kCtaSegSmem, "per-warp kept lists must fit the union");
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -204,86 +346,33 @@ __global__ void __launch_bounds__(kSegWarps * 32) nms_segment_kernel(const float
   const float4* boxes = cand_box + static_cast<size_t>(b) * anchors;
   const int* order = wk.order + static_cast<size_t>(b) * anchors;
   unsigned char* flags_img = wk.flags + static_cast<size_t>(b) * anchors;
-  const unsigned full = 0xffffffffu;
 
+  // ---- pass 1: one warp per small segment
+  for (int seg = blockIdx.x * kSegWarps + warp; seg < nseg; seg += gridDim.x * kSegWarps) {
+    const int s0 = wk.seg_start[b * static_cast<size_t>(anchors) + seg];
+    const int len = wk.seg_len[b * static_cast<size_t>(anchors) + seg];
+    if (len <= kWarpSegMax)
+      nms_warp_segment(boxes, order + s0, flags_img + s0, len, iou_thr, reinterpret_cast<float4*>(s_union) + warp * kWarpSegMax, lane);
+  }
+  // ---- pass 2: CTA-cooperative rounds for the large segments (boxes staged in shared memory when they fit)
+  __syncthreads();   // pass 1 is done with the shared-memory union
   for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
     const int s0 = wk.seg_start[b * static_cast<size_t>(anchors) + seg];
     const int len = wk.seg_len[b * static_cast<size_t>(anchors) + seg];
-    unsigned char* flags = flags_img + s0;   // bit0 = suppressed, bit1 = kept
-    const int* ord = order + s0;
-    if (threadIdx.x == 0) s_pos = 0;
-    __syncthreads();
-    while (true) {
-      if (warp == 0) {
-        // ---- gather the next <= 32 alive boxes in score order
-        int pos = s_pos, cnt = 0;
-        while (cnt < 32 && pos < len) {
-          const int pp = pos + lane;
-          const bool al = pp < len && (flags[pp] & 1) == 0;
-          const unsigned bal = __ballot_sync(full, al);
-          const int avail = __popc(bal);
-          const int take = min(avail, 32 - cnt);
-          const int rank = __popc(bal & ((1u << lane) - 1u));
-          if (al && rank < take) s_tilepos[cnt + rank] = pp;
-          if (take < avail) {
-            const unsigned last = __ballot_sync(full, al && rank == take - 1);
-            pos += __ffs(last);          // one past the last box taken
-          } else {
-            pos += 32;
-          }
-          cnt += take;
-        }
-        __syncwarp();
-        // ---- resolve the tile: lane i owns the i-th gathered box (all are alive on entry)
-        const bool has = lane < cnt;
-        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-        int my = 0;
-        if (has) {
-          my = s_tilepos[lane];
-          bi = boxes[ord[my]];
-        }
-        const float area_i = (bi.z - bi.x) * (bi.w - bi.y);
-        unsigned mask = 0;   // later in-tile boxes this box suppresses
-        for (int j = 1; j < cnt; ++j) {
-          float4 bj;
-          bj.x = __shfl_sync(full, bi.x, j);
-          bj.y = __shfl_sync(full, bi.y, j);
-          bj.z = __shfl_sync(full, bi.z, j);
-          bj.w = __shfl_sync(full, bi.w, j);
-          const float area_j = __shfl_sync(full, area_i, j);
-          if (j > lane && iou_gt(bi, area_i, bj, area_j, iou_thr)) mask |= 1u << j;
-        }
-        unsigned alive_bits = cnt >= 32 ? full : ((1u << cnt) - 1u);
-        for (int j = 0; j < cnt; ++j) {
-          const unsigned mj = __shfl_sync(full, mask, j);
-          if ((alive_bits >> j) & 1u) alive_bits &= ~mj;
-        }
-        const bool kept = has && ((alive_bits >> lane) & 1u);
-        if (has) flags[my] |= kept ? 2 : 1;
-        if (kept) s_kept[__popc(alive_bits & ((1u << lane) - 1u))] = bi;
-        if (lane == 0) {
-          s_pos = pos < len ? pos : len;
-          s_cnt = cnt;
-          s_nk = __popc(alive_bits);
-        }
+    if (len <= kWarpSegMax) continue;        // block-uniform
+    if (len <= kCtaSegSmem) {
+      float4* sb = reinterpret_cast<float4*>(s_union);
+      unsigned char* sf = s_union + kCtaSegSmem * sizeof(float4);
+      for (int i = threadIdx.x; i < len; i += kSegWarps * 32) {
+        sb[i] = boxes[order[s0 + i]];
+        sf[i] = 0;
       }
       __syncthreads();
-      const int cnt = s_cnt, nk = s_nk, pos = s_pos;
-      if (cnt == 0) break;
-      // ---- kept boxes of this round suppress the unvisited tail
-      for (int k = pos + threadIdx.x; k < len; k += kSegWarps * 32) {
-        if (flags[k] & 1) continue;
-        const float4 bk = boxes[ord[k]];
-        const float area_k = (bk.z - bk.x) * (bk.w - bk.y);
-        for (int j = 0; j < nk; ++j) {
-          const float4 bj = s_kept[j];
-          if (iou_gt(bj, (bj.z - bj.x) * (bj.w - bj.y), bk, area_k, iou_thr)) {
-            flags[k] |= 1;
-            break;
-          }
-        }
-      }
+      nms_cta_segment<true>(sb, nullptr, sf, len, iou_thr, s_kept, s_tilepos, s_ctl);
+      for (int i = threadIdx.x; i < len; i += kSegWarps * 32) flags_img[s0 + i] = sf[i];
       __syncthreads();
+    } else {
+      nms_cta_segment<false>(boxes, order + s0, flags_img + s0, len, iou_thr, s_kept, s_tilepos, s_ctl);
     }
   }
 }
