@@ -75,8 +75,9 @@ def test_sppf_pool_exact(B, H, W, c):
 
 
 # ------------------------------------------------------------------------------------------ decode
-def _run_decode(raw_nchw, nc, in_h, in_w):
-    """raw_nchw: list of 3 cpu f32 (B, 64+nc, h, w) -> dict of device outputs."""
+def _run_decode(raw_nchw, nc, in_h, in_w, full=True):
+    """raw_nchw: list of 3 cpu f32 (B, 64+nc, h, w) -> dict of device outputs.  full=False: NMS candidates only (the
+    kernel's logit-max fast path)."""
     _lib, L = _engine_parts()
     B = raw_nchw[0].shape[0]
     pitch = 64 + (nc + 15) // 16 * 16
@@ -94,7 +95,8 @@ def _run_decode(raw_nchw, nc, in_h, in_w):
                box=torch.zeros((B, A, 4)).cuda(), conf=torch.zeros((B, A)).cuda(),
                cls=torch.zeros((B, A), dtype=torch.int32).cuda())
     d.raw_pitch, d.batch, d.nc, d.in_h, d.in_w = pitch, B, nc, in_h, in_w
-    d.d_head_out, d.d_decoded = out["head"].data_ptr(), out["dec"].data_ptr()
+    if full:
+        d.d_head_out, d.d_decoded = out["head"].data_ptr(), out["dec"].data_ptr()
     d.d_cand_box, d.d_cand_conf, d.d_cand_cls = out["box"].data_ptr(), out["conf"].data_ptr(), out["cls"].data_ptr()
     _lib.check(L.tod_head_decode(C.byref(d), torch.cuda.current_stream().cuda_stream), "decode")
     torch.cuda.synchronize()
@@ -141,6 +143,36 @@ def test_decode_nc1_ragged_tiles():
     got = out["head"].cpu().numpy()
     assert np.abs(got[:, :4] - want[:, :4]).max() <= 2e-3 and np.abs(got[:, 4:] - want[:, 4:]).max() <= 2e-6
     assert int(out["cls"].abs().max()) == 0
+
+
+@pytest.mark.parametrize("nc", [80, 1, 3, 21, 200])
+def test_decode_candidates_only_path_equals_full_path_on_adversarial_logits(nc):
+    """The candidates-only kernel finds the class maximum on the logits and evaluates the sigmoid only inside a tie
+    window; it must give bit-identical (box, conf, cls) to the full path, whose conf/cls are checked against torch.max
+    over the kernel's own score tensor (lowest class wins ties): exact ties, near ties below float32 score resolution,
+    saturated logits (score 1.0 for many classes), hugely negative logits (score 0 for all) and +-inf."""
+    g = torch.Generator().manual_seed(11)
+    shapes = ((12, 20), (6, 10), (3, 5))
+    raw = [torch.randn((2, 64 + nc, h, w), generator=g) * 3 for h, w in shapes]
+    r0 = raw[0]
+    cls0 = r0[:, 64:]
+    if nc >= 3:
+        cls0[0, :, 0, 0] = -4.0; cls0[0, 2, 0, 0] = 1.5; cls0[0, 1, 0, 0] = 1.5          # exact tie: class 1 wins
+        cls0[0, :, 0, 1] = 20.0 + torch.arange(nc, dtype=torch.float32)                   # all saturate to 1.0: class 0
+        cls0[0, :, 0, 2] = -200.0                                                         # all scores 0: class 0
+        cls0[0, :, 0, 3] = 12.0; cls0[0, nc - 1, 0, 3] = 12.0000095                       # near tie, scores may collide
+        cls0[0, :, 0, 4] = 9.0; cls0[0, nc - 1, 0, 4] = 9.9                               # inside the wide window
+        cls0[0, :, 0, 5] = -3.0; cls0[0, nc - 1, 0, 5] = -3.0 + 2e-7                      # adjacent floats
+        cls0[0, :, 0, 6] = float("-inf"); cls0[0, 1, 0, 6] = -90.0
+        cls0[0, :, 0, 7] = 3.0; cls0[0, nc // 2, 0, 7] = float("inf")
+        cls0[1, :, 1, :] = torch.randint(-2, 3, (nc, 20), generator=g).float()            # many exact ties
+    full = _run_decode(raw, nc, 96, 160, full=True)
+    fast = _run_decode(raw, nc, 96, 160, full=False)
+    for k in ("box", "conf", "cls"):
+        assert torch.equal(full[k], fast[k]), k
+    conf, cls = full["dec"][:, :, 4:].max(2)
+    assert torch.equal(full["conf"], conf)
+    assert torch.equal(full["cls"].long(), cls)
 
 
 # ------------------------------------------------------------------------------------------ NMS
