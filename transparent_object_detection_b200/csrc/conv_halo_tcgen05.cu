@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) pdl_launch_dependents();   // the next kernel's prologue may overlap this grid's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected lane)
@@ -333,6 +334,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
             tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, (t * p.chunks + c) * p.block_k, n0);
           }
       }
+      // Everything above (and the weights just requested) is independent of earlier kernels.  Activations, residual
+      // and upsample-add operands and the output buffer are not: every access to them in this grid is ordered after
+      // this wait through the mbarrier chain that starts at the first A load below.
+      pdl_wait();
       int ai = 0, bi = 0;
       uint32_t pha = 0, phb = 0;   // ring phase bits
       const int n_it = sched.iters();
@@ -961,8 +966,10 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream) {
   grid -= grid % p.n_tiles;
   if (grid < p.n_tiles) grid = p.n_tiles;
   HaloKernel kern = halo_kernel(kvar);
-  kern<<<static_cast<unsigned>(grid), kHaloThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  TOD_CHECK_LAUNCH("conv_halo_tcgen05 launch");
+  if ((rc = check_cuda(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kHaloThreads), smem,
+                                  static_cast<cudaStream_t>(stream), p),
+                       "conv_halo_tcgen05 launch")) != TOD_OK)
+    return rc;
   return TOD_OK;
 }
 

@@ -150,10 +150,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) pdl_launch_dependents();   // the next kernel's prologue may overlap this grid's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected lane)
     if (elect_one()) {
+      // every access of this grid to data of earlier kernels (activations, residual / upsample-add, the output buffer)
+      // is ordered after this wait through the mbarrier chain that starts at the first load below
+      pdl_wait();
       int s = 0;         // ring slot and phase, continue across tiles
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -534,7 +538,9 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   p.total_tiles = static_cast<int>(m_tiles * p.n_tiles);
   const int slots = num_sms() * ctas_per_sm;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  conv_igemm_tcgen05<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  if ((rc = check_cuda(launch_pdl(conv_igemm_tcgen05, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), p),
+                       "conv_igemm_tcgen05 launch")) != TOD_OK)
+    return rc;
   TOD_CHECK_LAUNCH("conv_igemm_tcgen05 launch");
   return TOD_OK;
 }

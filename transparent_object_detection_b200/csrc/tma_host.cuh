@@ -1,7 +1,9 @@
 // Host-side helpers shared by the conv kernels: tensor-map encoding through the driver entry point, SM count.
 #pragma once
 
+#include <cstdlib>
 #include <mutex>
+#include <utility>
 
 #include "tod_common.cuh"
 
@@ -53,6 +55,32 @@ inline int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
     return TOD_ERR_CUDA;
   }
   return TOD_OK;
+}
+
+// Programmatic dependent launch is on unless TOD_PDL=0 (A/B measurements).  Kernels launched through launch_pdl call
+// pdl_wait() before they touch anything an earlier kernel of the stream wrote or still reads.
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TOD_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 inline int num_sms() {

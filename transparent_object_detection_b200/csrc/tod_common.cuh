@@ -119,6 +119,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// Programmatic dependent launch.  pdl_wait(): every grid this launch depends on has completed and its writes are visible
+// to this grid -- one thread suffices when every other thread of the grid reaches dependent data only through
+// synchronisation with it (mbarrier chains).  pdl_launch_dependents(): this CTA no longer holds back the launch of the
+// next kernel in the stream, whose prologue (barrier init, TMEM alloc, weight loads) then overlaps this grid's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
