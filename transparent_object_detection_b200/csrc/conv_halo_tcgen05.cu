@@ -21,6 +21,7 @@
 // warps 2..9 two epilogue groups that alternate over the two TMEM accumulator stages.
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "tma_host.cuh"
 
@@ -406,12 +407,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     uint32_t pha = 0, phb = 0;
     const uint32_t sub16 = p.sub_bytes >> 4;
     const uint32_t b_ring = smem_base + p.off_b;
-    const int gsz_ring = p.num_taps == 9 ? 3 : 1;   // taps per synchronisation group while weight tiles stream in
     const bool ks4 = p.ksteps == 4, ks2 = p.ksteps == 2;
     WaitClock wc(p.prof != nullptr && lane == 0);
     const long long role_t0 = wc.begin();
-    const bool trace = wc.on && blockIdx.x == 0;   // CTA 0 also records a per-group timeline
-    int ntrace = 0;
     const int n_it = sched.iters();
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it, ++lt) {
@@ -424,23 +422,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * acc_cols;
       const bool wait_b = !p.stationary || lt == 0;   // resident weights are only awaited on the first pass
-      // once the weights are resident and landed there is nothing to wait for between taps: one group per K chunk
-      const int gsz = wait_b ? gsz_ring : p.num_taps;
 #pragma unroll 1
       for (int c = 0; c < p.chunks; ++c) {
         const uint32_t a_base = smem_base + ai * p.a_slot_bytes;
-#pragma unroll 1
-        for (int t0 = 0; t0 < p.num_taps; t0 += gsz) {
-          // one overlapped wait for the group's weight tiles (and the A slot at the start of a chunk) ...
-          // (the host makes the ring size a multiple of gsz, so a group's slots are consecutive and share a phase)
+        // One synchronisation group = taps [T0, T0 + GSZ) of this chunk: an overlapped wait for the group's weight tiles
+        // (and the A slot at the start of a chunk), then GSZ * m * ksteps MMAs back to back.  T0 / GSZ are compile-time
+        // so that the per-tap descriptor offsets are constant-bank operands (statically indexed kernel parameters); read
+        // through a runtime tap index they were dependent ~50-cycle loads in front of every tap, and with N <= 64
+        // (<= 48 tensor cycles per MMA) the issuing thread, not the tensor pipe, was the limiter.
+        auto group = [&](auto t0c, auto gszc) {
+          constexpr int T0 = decltype(t0c)::value, GSZ = decltype(gszc)::value;
+          // (the host makes the ring size a multiple of the group size, so a group's slots are consecutive and share a phase)
           int slot0;
           uint32_t par_b = 0;
           if (p.stationary) {
-            slot0 = c * p.num_taps + t0;
+            slot0 = c * p.num_taps + T0;
           } else {
             slot0 = rbi;
             par_b = phb;
-            rbi += gsz;
+            rbi += GSZ;
             if (rbi == p.sb) {
               rbi = 0;
               phb ^= 1u;
@@ -454,17 +454,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
             bars[j + 1] = b_full0 + 8 * (slot0 + j);
             pars[j + 1] = par_b;
           }
-          const uint32_t mask = (t0 == 0 ? 1u : 0u) | (wait_b ? (gsz == 3 ? 14u : 2u) : 0u);
-          tw = wc.begin();
-          wait_set(bars, pars, mask);
-          wc.end(3, tw);
-          const long long t_ready = trace ? clock64() : 0;
+          const uint32_t mask = (T0 == 0 ? 1u : 0u) | (wait_b ? (GSZ == 3 ? 14u : 2u) : 0u);
+          long long tw2 = wc.begin();
+          if (mask != 0) wait_set(bars, pars, mask);
+          wc.end(3, tw2);
           tcgen05_fence_after();
-          // ... then gsz * m * ksteps MMAs back to back
           if (elect_one()) {
-#pragma unroll 1
-            for (int j = 0; j < gsz; ++j) {
-              const int t = t0 + j;
+#pragma unroll
+            for (int j = 0; j < GSZ; ++j) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const int t = T0 + j;                                   // compile-time after unrolling
               const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
               const uint32_t hi_a = p.tap_hi_a[t];
               const uint32_t b_lo = umma_desc_lo(b_ring + (slot0 + j) * p.b_slot_bytes);
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
                 const uint32_t al = a_lo + mt * sub16;
                 if (ks4) {
                   umma_bf16_k4(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
-                } else if (ks2) {   // 32-channel chunks: the rolled per-K loop below costs ~100 cycles per MMA in uniform-datapath latency
+                } else if (ks2) {   // 32-channel chunks
                   umma_bf16_k2(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
                 } else {
 #pragma unroll 1
@@ -485,19 +485,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
               }
               if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
             }
-            if (t0 + gsz >= p.num_taps) {
+            if (T0 + GSZ >= p.num_taps) {
               umma_commit(&a_empty[ai]);
               if (c == p.chunks - 1) umma_commit(&tmem_full_bar[acc]);
             }
           }
           __syncwarp();
-          if (trace && ntrace < 1024) {
-            unsigned long long* tr = p.prof + 148 * 16 + 3 * ntrace;
-            tr[0] = tw - role_t0;
-            tr[1] = t_ready - role_t0;
-            tr[2] = clock64() - role_t0;
-            ++ntrace;
+        };
+        using std::integral_constant;
+        if (p.num_taps == 9) {
+          if (wait_b) {
+            group(integral_constant<int, 0>{}, integral_constant<int, 3>{});
+            group(integral_constant<int, 3>{}, integral_constant<int, 3>{});
+            group(integral_constant<int, 6>{}, integral_constant<int, 3>{});
+          } else {   // resident weights that have landed: nothing to wait for between taps
+            group(integral_constant<int, 0>{}, integral_constant<int, 9>{});
           }
+        } else {
+          group(integral_constant<int, 0>{}, integral_constant<int, 1>{});
         }
         if (++ai == p.sa) {
           ai = 0;
@@ -508,7 +513,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     if (wc.on) {
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
-      if (trace) p.prof[148 * 16 + 3 * 1024] = ntrace;
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
@@ -527,6 +531,50 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const int sts_chunks = p.pb >> 4;       // 16-byte chunks per staging row (2, 4 or 8)
     WaitClock wc(p.prof != nullptr && leader);
     const long long role_t0 = wc.begin();
+    // tile coordinates of sub-tile s and this thread's row of the extra operand (null: row outside the tensor)
+    auto locate = [&](int s, int& c1, int& c2, int& c3, const void*& ex_row) {
+      ex_row = nullptr;
+      if (p.patch_mode) {
+        const int img = p.fd_tiles_per_img.div(s);
+        const int rem = s - img * p.tiles_per_img;
+        const int ti = p.fd_tiles_w.div(rem);
+        c1 = (rem - ti * p.tiles_w) * kPatchW;
+        c2 = ti * kPatchH;
+        c3 = img;
+        if (EXTRA != 0) {
+          const int h = c2 + (r >> 3), w = c1 + (r & 7);
+          if (h < p.hout && w < p.wout) {
+            if (EXTRA == 1)
+              ex_row = p.residual + ((static_cast<long long>(img) * p.hout + h) * p.wout + w) * p.res_pitch + n0;
+            else
+              ex_row = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
+          }
+        }
+      } else {
+        c1 = s * 128;
+        c2 = 0;
+        c3 = 0;
+        if (EXTRA != 0) {
+          const long long pix = static_cast<long long>(s) * 128 + r;
+          if (pix < p.mtot) {
+            if (EXTRA == 1) {
+              ex_row = p.residual + pix * p.res_pitch + n0;
+            } else {   // only the upsample-add needs (img, h, w) of a flat pixel index
+              const int ipix = static_cast<int>(pix);
+              const int img = p.fd_hw.div(ipix);
+              const int rem = ipix - img * (p.hout * p.wout);
+              const int h = p.fd_wout.div(rem);
+              const int w = rem - h * p.wout;
+              ex_row = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
+            }
+          }
+        }
+      }
+    };
+    // The extra operand was written by an earlier kernel and its first chunk is requested BEFORE the accumulator wait
+    // (the loads do not depend on this grid's MMAs), so these threads order themselves after the earlier grids directly.
+    if (EXTRA != 0) pdl_wait();
+    const int first_cols = min(32, p.block_n);
     uint32_t lt = 0;
     const int n_it = sched.iters();
 #pragma unroll 1
@@ -534,55 +582,28 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       if ((lt & 1) != static_cast<uint32_t>(group)) continue;
       int s0, m_cur;
       sched.get(it, s0, m_cur);
+      int nc1 = 0, nc2 = 0, nc3 = 0;
+      const void* nrow = nullptr;
+      ExtraRegs<EXTRA> exn;                  // first chunk of the coming sub-tile's extra operand
+      locate(s0, nc1, nc2, nc3, nrow);
+      if (EXTRA != 0 && nrow != nullptr) exn.load(nrow, 0, first_cols);
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
       wc.end(1, tw);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < m_cur; ++mt) {
-        const int s = s0 + mt;
-        int c1, c2, c3;
-        const void* ex_row = nullptr;       // this thread's row of the extra operand (null: row outside the tensor)
-        if (p.patch_mode) {
-          const int img = p.fd_tiles_per_img.div(s);
-          const int rem = s - img * p.tiles_per_img;
-          const int ti = p.fd_tiles_w.div(rem);
-          c1 = (rem - ti * p.tiles_w) * kPatchW;
-          c2 = ti * kPatchH;
-          c3 = img;
-          if (EXTRA != 0) {
-            const int h = c2 + (r >> 3), w = c1 + (r & 7);
-            if (h < p.hout && w < p.wout) {
-              if (EXTRA == 1)
-                ex_row = p.residual + ((static_cast<long long>(img) * p.hout + h) * p.wout + w) * p.res_pitch + n0;
-              else
-                ex_row = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
-            }
-          }
-        } else {
-          c1 = s * 128;
-          c2 = 0;
-          c3 = 0;
-          if (EXTRA != 0) {
-            const long long pix = static_cast<long long>(s) * 128 + r;
-            if (pix < p.mtot) {
-              if (EXTRA == 1) {
-                ex_row = p.residual + pix * p.res_pitch + n0;
-              } else {   // only the upsample-add needs (img, h, w) of a flat pixel index
-                const int ipix = static_cast<int>(pix);
-                const int img = p.fd_hw.div(ipix);
-                const int rem = ipix - img * (p.hout * p.wout);
-                const int h = p.fd_wout.div(rem);
-                const int w = rem - h * p.wout;
-                ex_row = p.upadd + ((static_cast<long long>(img) * (p.hout >> 1) + (h >> 1)) * (p.wout >> 1) + (w >> 1)) * p.cout + n0;
-              }
-            }
-          }
-        }
+        const int c1 = nc1, c2 = nc2, c3 = nc3;
+        const void* ex_row = nrow;
         const bool ex_valid = ex_row != nullptr;
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
         ExtraRegs<EXTRA> ex[kChunks];
-        bool ex0_ready = false;             // ex[0] already holds the first chunk of the coming panel
+        ex[0] = exn;
+        bool ex0_ready = true;              // ex[0] already holds the first chunk of the coming panel
+        if (mt + 1 < m_cur) {               // request the next sub-tile's first chunk a whole sub-tile ahead
+          locate(s0 + mt + 1, nc1, nc2, nc3, nrow);
+          if (EXTRA != 0 && nrow != nullptr) exn.load(nrow, 0, first_cols);
+        }
 #pragma unroll 1
         for (int pn = 0; pn < npanels; ++pn) {
           const int col0 = pn * p.pc;
