@@ -11,8 +11,9 @@ One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); every rank runs 
   e2e          same metric through the public API Detector.submit / Detector.collect (two batches in flight): pinned
                host uint8 (B, H, W, 3) batch -> H2D -> graph -> D2H of counts and kept rows, every step;
                e2e.f32_input is the synchronous Detector.detect on the reference's float32 (B, 3, H, W) tensor
-  roofline     the dominant kernel (conv_halo_tcgen05, all conv launches of one pass) against the measured
-               bf16 tensor peak: algorithmic conv FLOPs / summed conv launch time (CUDA events, eager pass)
+  roofline     the dominant kernel (the tcgen05 conv kernels, all conv launches of one pass) against the measured
+               bf16 tensor peak: algorithmic conv FLOPs / summed conv launch time (CUDA events, eager pass);
+               traffic = measured DRAM bytes per conv launch from the committed ncu pass (profiles/conv_dram_traffic.json)
   cpu_baseline the CPU oracle (port of the reference path) on this box's host cores, bounded sample
   --impl reference   times the CPU oracle alone (the reference itself cannot travel to the GPU box)
 """
@@ -287,7 +288,7 @@ def main():
                 traffic = float(json.load(open(tpath))["avg_bytes_per_launch"])
             except Exception:
                 traffic = None
-        roof = {"bound": "tensor", "kernel": "conv_halo_tcgen05", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": "conv_halo_tcgen05 / conv_igemm_tcgen05 (all conv launches of one pass)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                 "launches": len(conv_rows), "flop_per_launch_avg": conv_gflop * 1e9 / max(len(conv_rows), 1),
                 "avg_launch_ms": conv_ms / max(len(conv_rows), 1), "conv_share_of_eager_pass": conv_ms / all_ms if all_ms else None}
