@@ -76,6 +76,33 @@ typedef struct tod_conv_desc {
 
 int tod_conv2d_nhwc_bf16(const tod_conv_desc* desc, void* stream);
 
+/*
+ * The last conv of a head tower fused with the head decode (detect path: only NMS candidates are needed).
+ * Replaces, in one launch and without materialising the raw (64 + nc)-channel maps: the bare 1x1 conv + bias
+ * model/head.py:31 (box tower) or :42 (class tower) together with its share of Head.forward's eval branch
+ * model/head.py:53-61, DFL.forward model/blocks.py:154-157, make_anchors utils/bbox_utils.py:14-37,
+ * DecodeBox.decode_box :77-82 and the corner conversion / class max of non_max_suppression :144-153.
+ *   mode TOD_FUSE_BOX: conv cout must be 64 (4 x 16 DFL bins)  -> d_cand_box f32 [batch, A, 4]
+ *   mode TOD_FUSE_CLS: conv cout >= nc (padded to 16)          -> d_cand_conf f32 [batch, A], d_cand_cls i32 [batch, A]
+ * desc must be a 1x1, stride 1, act NONE conv (d_out is ignored and may be NULL); level_off is the index of the
+ * level's first anchor among the A anchors of an image, stride = in_h / hin.  The candidates are bit-identical to
+ * tod_conv2d_nhwc_bf16 (f32 out) followed by tod_head_decode.
+ */
+enum { TOD_FUSE_BOX = 1, TOD_FUSE_CLS = 2 };
+typedef struct tod_head_fuse_desc {
+  int32_t mode;
+  int32_t nc;
+  int32_t level_off, anchors;
+  int32_t in_h, in_w;
+  float stride;
+  float* d_cand_box;
+  float* d_cand_conf;
+  int32_t* d_cand_cls;
+  int32_t reserved[4];
+} tod_head_fuse_desc;
+
+int tod_conv2d_head_decode(const tod_conv_desc* desc, const tod_head_fuse_desc* fuse, void* stream);
+
 /* Packed-weight geometry for a conv: *block_k (TMA/UMMA K chunk), *cin_pad (cin rounded up to block_k),
  * *k_total = ksize*ksize*cin_pad.  Host packers lay weights out as [cout][tap][cin_pad] bf16, zero padded. */
 int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_k_hint,

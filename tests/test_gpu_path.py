@@ -330,6 +330,31 @@ def test_detector_graph_matches_eager_and_oracle_nms():
     assert any(w is not None for w in want)
 
 
+def test_fused_head_decode_equals_conv_then_decode_bit_for_bit():
+    """tod_conv2d_head_decode (last conv of a head tower + its share of the decode in the conv epilogue) must give
+    exactly the candidates of the unfused path (f32 raw maps -> tod_head_decode), at a batch / size whose flat 128-row
+    tiles straddle images and end in a partial tile."""
+    from oracle import synth
+    from transparent_object_detection_b200 import BaseModel
+    C_, d, m = synth.SCALES["n"]
+    model = BaseModel(80, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    eng = model.engine(3, 96, 160)
+    x = torch.from_numpy(synth.make_images_u8(3, 96, 160, seed=5)).cuda()
+    eng.run_network(x)
+    eng.run_decode(False, False, True)
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (eng.cand_box, eng.cand_conf, eng.cand_cls)]
+    for t in (eng.cand_box, eng.cand_conf, eng.cand_cls):
+        t.fill_(-7)
+    eng.run_network(x, fused_decode=True)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.cand_cls, want[2])
+    assert torch.equal(eng.cand_conf, want[1])
+    assert torch.equal(eng.cand_box, want[0])
+    assert float(want[1].max()) > 0 and int(want[2].max()) > 0
+
+
 # ------------------------------------------------------------------------------------------ uint8 input path
 @pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 32), (1, 32, 32, 16), (1, 640, 640, 32), (3, 38, 50, 64), (1, 64, 64, 128)])
 def test_stem_u8_tensor_core(B, H, W, cout):

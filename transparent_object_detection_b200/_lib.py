@@ -41,6 +41,18 @@ class DecodeDesc(C.Structure):
     ]
 
 
+class HeadFuseDesc(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("nc", C.c_int32), ("level_off", C.c_int32), ("anchors", C.c_int32),
+        ("in_h", C.c_int32), ("in_w", C.c_int32), ("stride", C.c_float),
+        ("d_cand_box", C.c_void_p), ("d_cand_conf", C.c_void_p), ("d_cand_cls", C.c_void_p),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+TOD_FUSE_BOX, TOD_FUSE_CLS = 1, 2
+
+
 class TodError(RuntimeError):
     pass
 
@@ -62,6 +74,7 @@ def lib() -> C.CDLL:
     L.tod_device_ok.restype = C.c_int
     L.tod_conv2d_nhwc_bf16.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
     L.tod_conv2d_nhwc_bf16_simt_check.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
+    L.tod_conv2d_head_decode.argtypes = [C.POINTER(ConvDesc), C.POINTER(HeadFuseDesc), C.c_void_p]
     L.tod_conv_weight_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32)]
     L.tod_stem_conv_nchw_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -23,6 +23,7 @@
 #include <mutex>
 #include <type_traits>
 
+#include "decode_math.cuh"
 #include "tma_host.cuh"
 
 namespace tod {
@@ -95,6 +96,12 @@ struct __align__(64) HaloParams {
   int res_pitch;
   int act, out_f32;
   int pc, pb, smask;         // panel columns, panel row bytes, swizzle XOR mask (7 / 3 / 1)
+  // fused head decode (EXTRA 3: box tower output -> cand_box, EXTRA 4: class tower output -> cand_conf / cand_cls)
+  int dec_nc, dec_level_off, dec_anchors;
+  float dec_stride, dec_in_w, dec_in_h;
+  float* cand_box;
+  float* cand_conf;
+  int* cand_cls;
   unsigned long long* prof;  // optional per-CTA wait counters (tools/conv_profile.py), null in production
 };
 
@@ -516,7 +523,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
-    static_assert(!(OUT_F32 && EXTRA != 0), "extra operands are only combined with bf16 output");
+    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2)), "extra operands are only combined with bf16 output");
+    static_assert(EXTRA < 3 || (OUT_F32 && !SILU), "the fused head decode consumes the f32 logits of a bare 1x1 conv");
     constexpr int kPanelCols = OUT_F32 ? 32 : 64;      // a full staging panel row is 128 bytes
     constexpr int kChunks = kPanelCols / 32;           // 32-column chunks per panel
     constexpr int kWordsPerChunk = OUT_F32 ? 32 : 16;  // packed output words of one chunk
@@ -531,6 +539,113 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const int sts_chunks = p.pb >> 4;       // 16-byte chunks per staging row (2, 4 or 8)
     WaitClock wc(p.prof != nullptr && leader);
     const long long role_t0 = wc.begin();
+    if constexpr (EXTRA >= 3) {
+      // ---------------------------------------------------------------- fused head decode (flat 1x1 mode only)
+      // The last conv of a head tower writes no logits: this thread owns one anchor row of the accumulator and reduces it
+      // on the spot -- DFL + anchor/stride decode -> NMS corners (EXTRA 3), or class max on the logits -> (score, class)
+      // (EXTRA 4) -- with the arithmetic of head_decode_kernel (decode_math.cuh), so the candidates are bit-identical to
+      // the unfused path.  No staging panel, no TMA store, no block barriers.
+      uint32_t lt = 0;
+      const int n_it = sched.iters();
+      const int hw = p.hout * p.wout;
+#pragma unroll 1
+      for (int it = 0; it < n_it; ++it, ++lt) {
+        if ((lt & 1) != static_cast<uint32_t>(group)) continue;
+        int s0, m_cur;
+        sched.get(it, s0, m_cur);
+        wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int mt = 0; mt < m_cur; ++mt) {
+          const long long pix = static_cast<long long>(s0 + mt) * 128 + r;
+          const bool valid = pix < p.mtot;
+          const int ipix = valid ? static_cast<int>(pix) : 0;
+          const int img = p.fd_hw.div(ipix);
+          const int a = ipix - img * hw;                      // anchor inside the level
+          const size_t g = static_cast<size_t>(img) * p.dec_anchors + p.dec_level_off + a;
+          const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
+          if (EXTRA == 3) {
+            float dist[4];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr0 + ch * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int sd = 0; sd < 2; ++sd) {
+                float l[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) l[i] = __fadd_rn(__uint_as_float(v[sd * 16 + i]), bias_s[ch * 32 + sd * 16 + i]);
+                dist[ch * 2 + sd] = dfl_side(l);
+              }
+            }
+            if (mt == m_cur - 1) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+            }
+            if (valid) {
+              const int gy = p.fd_wout.div(a), gx = a - gy * p.wout;
+              const float4 bpx = box_xywh_px(dist[0], dist[1], dist[2], dist[3], gx, gy, p.dec_stride);
+              reinterpret_cast<float4*>(p.cand_box)[g] = box_corners_norm(bpx, p.dec_in_w, p.dec_in_h);
+            }
+          } else {
+            // fn(logit, class, j) over this anchor's nc classes; j = class & 3 lets the caller keep four independent
+            // dependency chains (a single running top-2 is a serial chain of ~5 instructions per class and the eight
+            // epilogue warps of a CTA cannot hide it)
+            auto scan = [&](auto&& fn) {
+#pragma unroll 1
+              for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                uint32_t v[32];
+                if (p.block_n - c0 >= 32) {
+                  tmem_ld_32x32b_x32(taddr0 + c0, v);
+                } else {
+                  tmem_ld_32x32b_x16(taddr0 + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+#pragma unroll
+                  for (int i = 16; i < 32; ++i) v[i] = 0;
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (c0 + i + e < p.dec_nc) fn(__fadd_rn(__uint_as_float(v[i + e]), bb[e]), c0 + i + e, e);
+                }
+              }
+            };
+            LogitTop2 tops[4];
+            scan([&](float x, int c, int j) { tops[j].add(x, c); });
+            tops[0].merge(tops[1]);
+            tops[2].merge(tops[3]);
+            tops[0].merge(tops[2]);
+            const LogitTop2 top = tops[0];
+            const float thr_logit = tie_window_threshold(top.x1);
+            float best = -1.0f;
+            int bi = 0x7fffffff;
+            // rare: several logits of some row inside its tie window -> evaluate them all.  tcgen05.ld is warp-collective,
+            // so the rescan is decided per warp; rows that do not need it keep their single-candidate result.
+            const bool rescan = top.x2 >= thr_logit;
+            if (__any_sync(0xffffffffu, rescan))
+              scan([&](float x, int c, int) { if (rescan && x >= thr_logit) better(best, bi, sigmoid_ref(x), c); });
+            if (!rescan && top.x1 >= thr_logit) {
+              best = sigmoid_ref(top.x1);
+              bi = top.c1;
+            }
+            if (mt == m_cur - 1) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+            }
+            if (valid) {
+              p.cand_conf[g] = best;
+              p.cand_cls[g] = bi;
+            }
+          }
+        }
+      }
+    } else {
     // tile coordinates of sub-tile s and this thread's row of the extra operand (null: row outside the tensor)
     auto locate = [&](int s, int& c1, int& c2, int& c3, const void*& ex_row) {
       ex_row = nullptr;
@@ -674,6 +789,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 8 + group * 4 + i] = wc.acc[i];
     }
+    }   // EXTRA < 3
   }
 
   tcgen05_fence_before();
@@ -815,7 +931,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     const bool ok = make_fd(p.tiles_per_img, p.num_subtiles, &p.fd_tiles_per_img) &&
                     make_fd(p.tiles_w, p.tiles_per_img, &p.fd_tiles_w) &&
                     make_fd(wout, static_cast<long long>(hout) * wout, &p.fd_wout) &&
-                    (d->d_upadd == nullptr || make_fd(static_cast<long long>(hout) * wout, mtot, &p.fd_hw));
+                    make_fd(static_cast<long long>(hout) * wout, mtot, &p.fd_hw);
     TOD_CHECK_ARG(ok, "conv: problem too large for the tile index arithmetic");
   }
   {
@@ -940,9 +1056,9 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 }
 
 // kernel variants: [0..2] bf16 out, no activation, extra 0/1/2; [3..5] bf16 out, SiLU, extra 0/1/2; [6] f32 out, no
-// activation; [7] f32 out, SiLU
+// activation; [7] f32 out, SiLU; [8] fused box decode; [9] fused class decode
 using HaloKernel = void (*)(HaloParams);
-constexpr int kHaloVariants = 8;
+constexpr int kHaloVariants = 10;
 static HaloKernel halo_kernel(int i) {
   switch (i) {
     case 0: return conv_halo_tcgen05<false, false, 0>;
@@ -952,11 +1068,13 @@ static HaloKernel halo_kernel(int i) {
     case 4: return conv_halo_tcgen05<true, false, 1>;
     case 5: return conv_halo_tcgen05<true, false, 2>;
     case 6: return conv_halo_tcgen05<false, true, 0>;
-    default: return conv_halo_tcgen05<true, true, 0>;
+    case 7: return conv_halo_tcgen05<true, true, 0>;
+    case 8: return conv_halo_tcgen05<false, true, 3>;
+    default: return conv_halo_tcgen05<false, true, 4>;
   }
 }
 
-int conv_halo_launch(const tod_conv_desc* d, void* stream) {
+int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_desc* fuse) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -969,7 +1087,21 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream) {
   const int extra = d->d_residual != nullptr ? 1 : (d->d_upadd != nullptr ? 2 : 0);
   TOD_CHECK_ARG(!(d->d_residual != nullptr && d->d_upadd != nullptr), "conv: residual and upsample-add are mutually exclusive");
   TOD_CHECK_ARG(!(f32 && extra != 0), "conv: residual / upsample-add need bf16 output");
-  const int kvar = f32 ? (silu ? 7 : 6) : ((silu ? 3 : 0) + extra);
+  int kvar = f32 ? (silu ? 7 : 6) : ((silu ? 3 : 0) + extra);
+  if (fuse != nullptr) {
+    TOD_CHECK_ARG(d->ksize == 1 && !silu && extra == 0, "fused head decode: needs a bare 1x1 conv (no activation, no extra operand)");
+    TOD_CHECK_ARG(fuse->mode == TOD_FUSE_BOX || fuse->mode == TOD_FUSE_CLS, "fused head decode: bad mode %d", fuse->mode);
+    TOD_CHECK_ARG(fuse->mode != TOD_FUSE_BOX || (d->cout == 64 && fuse->d_cand_box != nullptr &&
+                                                 (reinterpret_cast<uintptr_t>(fuse->d_cand_box) & 15) == 0),
+                  "fused box decode: needs cout 64 and a 16-byte aligned cand_box");
+    TOD_CHECK_ARG(fuse->mode != TOD_FUSE_CLS || (fuse->nc > 0 && fuse->nc <= d->cout && d->cout <= 256 &&
+                                                 fuse->d_cand_conf != nullptr && fuse->d_cand_cls != nullptr),
+                  "fused class decode: needs 0 < nc <= cout <= 256 and cand_conf / cand_cls");
+    TOD_CHECK_ARG(fuse->anchors > 0 && fuse->level_off >= 0 && fuse->level_off + d->hin * d->win <= fuse->anchors &&
+                      fuse->in_h > 0 && fuse->in_w > 0 && fuse->stride > 0.0f,
+                  "fused head decode: bad anchor geometry");
+    kvar = fuse->mode == TOD_FUSE_BOX ? 8 : 9;
+  }
 
   HaloParams p;
   size_t smem = 0;
@@ -981,6 +1113,18 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream) {
   TOD_CHECK_ARG(fits, "conv: no shared-memory plan fits (cin %d cout %d ksize %d stride %d)", d->cin, d->cout, d->ksize,
                 d->stride);
 
+  if (fuse != nullptr) {
+    TOD_CHECK_ARG(p.n_tiles == 1 && !p.patch_mode, "fused head decode: unexpected tiling");
+    p.dec_nc = fuse->nc;
+    p.dec_level_off = fuse->level_off;
+    p.dec_anchors = fuse->anchors;
+    p.dec_stride = fuse->stride;
+    p.dec_in_w = static_cast<float>(fuse->in_w);
+    p.dec_in_h = static_cast<float>(fuse->in_h);
+    p.cand_box = fuse->d_cand_box;
+    p.cand_conf = fuse->d_cand_conf;
+    p.cand_cls = fuse->d_cand_cls;
+  }
   const long long work = static_cast<long long>(p.num_super) * p.n_tiles;
   long long grid = num_sms();
   if (grid > work) grid = work;

@@ -348,9 +348,9 @@ static void pick_patch(int hout, int wout, int* th, int* tw) {
   *tw = btw;
 }
 
-static int validate(const tod_conv_desc* d) {
+static int validate(const tod_conv_desc* d, bool need_out = true) {
   TOD_CHECK_ARG(d != nullptr, "conv: null descriptor");
-  TOD_CHECK_ARG(d->d_x && d->d_w && d->d_out, "conv: null x/w/out pointer");
+  TOD_CHECK_ARG(d->d_x && d->d_w && (d->d_out || !need_out), "conv: null x/w/out pointer");
   TOD_CHECK_ARG(d->batch > 0 && d->hin > 0 && d->win > 0, "conv: bad shape %d x %d x %d", d->batch, d->hin, d->win);
   TOD_CHECK_ARG((d->ksize == 1 && d->stride == 1) || (d->ksize == 3 && (d->stride == 1 || d->stride == 2)),
                 "conv: unsupported ksize %d stride %d", d->ksize, d->stride);
@@ -385,6 +385,17 @@ extern "C" int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_
   if (cin_pad) *cin_pad = cp;
   if (k_total) *k_total = ksize * ksize * cp;
   return TOD_OK;
+}
+
+extern "C" int tod_conv2d_head_decode(const tod_conv_desc* d, const tod_head_fuse_desc* fuse, void* stream) {
+  TOD_CHECK_ARG(fuse != nullptr, "fused head decode: null descriptor");
+  int rc = validate(d, false);
+  if (rc != TOD_OK) return rc;
+  tod_conv_desc c = *d;
+  c.out_dtype = TOD_OUT_F32;             // the logits stay f32 (TMEM) and never reach memory
+  if (c.d_out == nullptr) c.d_out = const_cast<void*>(c.d_x);   // only used to build an (unused) output tensor map
+  if (c.out_pitch < c.cout) c.out_pitch = c.cout;
+  return conv_halo_launch(&c, stream, fuse);
 }
 
 extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {

@@ -6,7 +6,7 @@
 // Arithmetic follows SURVEY.md Appendix B step by step in fp32 (true divisions, no FMA contraction:
 // this file is compiled with -fmad=false).  HBM-bound: reads (64+nc) f32 per anchor, writes up to
 // 2*(4+nc)+6 f32 per anchor; every global access is a coalesced row segment.
-#include "tod_common.cuh"
+#include "decode_math.cuh"
 
 namespace tod {
 
@@ -27,13 +27,6 @@ struct DecodeParams {
   float* cand_conf;
   int* cand_cls;
 };
-
-__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }   // Tensor.sigmoid(), head.py:61
-
-// (score, class) candidates are ordered by score descending, then class ascending (torch.max keeps the first maximum)
-__device__ __forceinline__ void better(float& s, int& c, float s2, int c2) {
-  if (s2 > s || (s2 == s && c2 < c)) { s = s2; c = c2; }
-}
 
 // Four threads per anchor row (64 + nc f32 logits), 64 anchors per CTA.  Thread (a, j): DFL of box side j (16 bins,
 // 64 contiguous bytes) and a contiguous quarter of the class logits, so the four threads of an anchor read one
@@ -79,14 +72,7 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
       const float4 v = __ldg(row + side * 4 + i);
       l[4 * i] = v.x; l[4 * i + 1] = v.y; l[4 * i + 2] = v.z; l[4 * i + 3] = v.w;
     }
-    float m = l[0];
-#pragma unroll
-    for (int i = 1; i < 16; ++i) m = fmaxf(m, l[i]);
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { l[i] = expf(l[i] - m); sum += l[i]; }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dist += static_cast<float>(i) * (l[i] / sum);   // softmax, then arange(16) projection
+    dist = dfl_side(l);
   }
   // ---- classes
   float best = -1.0f;
@@ -108,28 +94,21 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
       }
   } else {
     // the two largest logits of this thread (first occurrence wins ties, like the ascending-class scan of the scores)
-    float x1 = ninf, x2 = ninf;
-    int c1 = 0x7fffffff;
+    LogitTop2 top;
     if (valid)
       for (int k = k0; k < k1; ++k) {
         const float4 v = __ldg(row + 16 + k);
         const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 4 * k + e;
-          if (c < p.nc) {
-            const float x = xs[e];
-            if (x > x1) { x2 = x1; x1 = x; c1 = c; }
-            else x2 = fmaxf(x2, x);
-          }
-        }
+        for (int e = 0; e < 4; ++e)
+          if (4 * k + e < p.nc) top.add(xs[e], 4 * k + e);
       }
+    const float x1 = top.x1, x2 = top.x2;
+    const int c1 = top.c1;
     float m = x1;
     m = fmaxf(m, __shfl_xor_sync(full, m, 1));
     m = fmaxf(m, __shfl_xor_sync(full, m, 2));
-    // float32 scores of two logits can only tie when the logits are this close (d sigmoid / dx = s (1 - s));
-    // outside (-80, 15) the sigmoid saturates and every class is evaluated
-    const float thr_logit = (m > -80.0f && m < 15.0f) ? m - (m > 8.0f ? 2.0f : 0.01f) : ninf;
+    const float thr_logit = tie_window_threshold(m);
     if (valid) {
       if (x2 >= thr_logit) {                 // rare: more than one of this thread's logits in the window -> rescan
         for (int k = k0; k < k1; ++k) {
@@ -162,10 +141,8 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
   if (side == 0 && valid) {
     const int ai = a0 + a;
     const int gy = ai / lw, gx = ai - gy * lw;
-    const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;  // make_anchors
-    const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;                 // head.py:57-58
-    const float bx = ((x1 + x2) / 2.0f) * stride, by = ((y1 + y2) / 2.0f) * stride;     // head.py:59-61
-    const float bw = (x2 - x1) * stride, bh = (y2 - y1) * stride;
+    const float4 bpx = box_xywh_px(dl, dt, dr, db, gx, gy, stride);
+    const float bx = bpx.x, by = bpx.y, bw = bpx.z, bh = bpx.w;
     if (FULL) {
       s_box[a * 4 + 0] = bx;
       s_box[a * 4 + 1] = by;
@@ -177,8 +154,7 @@ __global__ void __launch_bounds__(kDecThreads) head_decode_kernel(const DecodePa
       const size_t g = static_cast<size_t>(b) * p.anchors + ag0 + a;
       p.cand_conf[g] = best;
       p.cand_cls[g] = bi;
-      const float nx = bx / p.in_w, ny = by / p.in_h, nw = bw / p.in_w, nh = bh / p.in_h;
-      reinterpret_cast<float4*>(p.cand_box)[g] = make_float4(nx - nw / 2.0f, ny - nh / 2.0f, nx + nw / 2.0f, ny + nh / 2.0f);
+      reinterpret_cast<float4*>(p.cand_box)[g] = box_corners_norm(bpx, p.in_w, p.in_h);
     }
   }
   if (!FULL) return;

@@ -22,7 +22,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, DecodeDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_OUT_BF16, TOD_OUT_F32, check
+from ._lib import (ConvDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16,
+                   TOD_OUT_F32, check)
 
 BN_EPS = 1e-5
 
@@ -264,6 +265,20 @@ class DetectorEngine:
         self.keep_count = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.dets = torch.zeros((B, A, 6), dtype=torch.float32, device=dev)
         self.launches_forward = len(self.ops)
+        # fused head outputs (detect path): the last conv of each tower decodes its own accumulator rows into the NMS
+        # candidates (tod_conv2d_head_decode); the raw maps and the decode kernel are then not needed
+        self.head_fuse: Dict[str, HeadFuseDesc] = {}
+        off = 0
+        for i, (h, w) in enumerate(self.level_shapes):
+            for tower, mode in (("box", TOD_FUSE_BOX), ("cls", TOD_FUSE_CLS)):
+                f = HeadFuseDesc()
+                f.mode, f.nc, f.level_off, f.anchors = mode, nc, off, A
+                f.in_h, f.in_w, f.stride = H, W, float(H // h)
+                f.d_cand_box, f.d_cand_conf, f.d_cand_cls = (self.cand_box.data_ptr(), self.cand_conf.data_ptr(),
+                                                             self.cand_cls.data_ptr())
+                self.head_fuse[f"head.{tower}.{i}.4"] = f
+            off += h * w
+        self.fuse_head_decode = True    # graph_for: candidates straight from the head convs
 
     # ------------------------------------------------------------------ execution
     def _stream(self) -> int:
@@ -287,12 +302,13 @@ class DetectorEngine:
             self._slot_out[slot] = (torch.zeros_like(self.keep_count), torch.zeros_like(self.dets))
         return self._slot_out[slot]
 
-    def run_network(self, x: Optional[torch.Tensor] = None, fork: bool = False) -> None:
+    def run_network(self, x: Optional[torch.Tensor] = None, fork: bool = False, fused_decode: bool = False) -> None:
         """Enqueue stem + every conv + SPPF pooling (the raw head maps land in self.raw).
         x: float32 (B, 3, H, W) in [0, 1]  or  uint8 (B, H, W, 3).
         fork: issue the six head towers (box / cls x three levels, mutually independent: model/head.py:24-44) on side
         streams as soon as their input feature exists, so that they overlap the rest of the neck and one another
-        (used inside graph capture, where the forks become parallel graph branches)."""
+        (used inside graph capture, where the forks become parallel graph branches).
+        fused_decode: the last conv of every head tower writes the NMS candidates itself (no raw maps, no run_decode)."""
         main = torch.cuda.current_stream(self.device)
         L = self.L
         if x is None:
@@ -304,7 +320,10 @@ class DetectorEngine:
         def issue(kind, name, payload, stream):
             st = stream.cuda_stream
             if kind == "conv":
-                check(L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
+                if fused_decode and name in self.head_fuse:
+                    check(L.tod_conv2d_head_decode(C.byref(payload), C.byref(self.head_fuse[name]), st), name)
+                else:
+                    check(L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
             elif kind == "stem":
                 w, b, out = payload
                 fn = L.tod_stem_conv_nhwc_u8 if u8 else L.tod_stem_conv_nchw_f32
@@ -367,7 +386,7 @@ class DetectorEngine:
     # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
     @property
     def launches_per_pass(self) -> int:
-        return len(self.ops) + 1 + 3
+        return len(self.ops) + (0 if self.fuse_head_decode else 1) + 3
 
     def capture(self, conf_thres: float, nms_thres: float, head_out: bool = False, decoded: bool = False) -> None:
         """Capture network + decode + NMS on the static input into one CUDA graph."""
@@ -402,8 +421,9 @@ class DetectorEngine:
         cnt, dets = self.slot_outputs(slot)
 
         def body():
-            self.run_network(x, fork=self.fork_head)
-            self.run_decode(False, False, True)
+            self.run_network(x, fork=self.fork_head, fused_decode=self.fuse_head_decode)
+            if not self.fuse_head_decode:
+                self.run_decode(False, False, True)
             self.run_nms(conf_thres, nms_thres)
             cnt.copy_(self.keep_count)
             dets.copy_(self.dets)
