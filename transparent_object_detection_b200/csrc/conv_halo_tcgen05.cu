@@ -408,14 +408,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
+    // ------------------------------------------------------------------ MMA issuer: ONE elected lane runs the whole role
+    // (waits and issue).  Warp-level waits + elect + __syncwarp around every tap group cost ~430 cycles per group in
+    // which the 8-deep MMA queue (<= 512 tensor cycles at N = 128) drained: the tensor pipe was busy 66 % on the
+    // weight-streaming layers.
+    if (elect_one()) {
     uint32_t lt = 0;
     int ai = 0, rbi = 0;
     uint32_t pha = 0, phb = 0;
     const uint32_t sub16 = p.sub_bytes >> 4;
     const uint32_t b_ring = smem_base + p.off_b;
     const bool ks4 = p.ksteps == 4, ks2 = p.ksteps == 2;
-    WaitClock wc(p.prof != nullptr && lane == 0);
+    WaitClock wc(p.prof != nullptr);
     const long long role_t0 = wc.begin();
     const int n_it = sched.iters();
 #pragma unroll 1
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           if (mask != 0) wait_set(bars, pars, mask);
           wc.end(3, tw2);
           tcgen05_fence_after();
-          if (elect_one()) {
+          {
 #pragma unroll
             for (int j = 0; j < GSZ; ++j) {
               constexpr int dummy = 0;
@@ -497,7 +501,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
               if (c == p.chunks - 1) umma_commit(&tmem_full_bar[acc]);
             }
           }
-          __syncwarp();
         };
         using std::integral_constant;
         if (p.num_taps == 9) {
@@ -521,6 +524,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
     }
+    }   // elected lane
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
     static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2)), "extra operands are only combined with bf16 output");
