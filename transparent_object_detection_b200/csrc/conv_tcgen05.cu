@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one lane issues)
+    // ------------------------------------------------------------------ MMA issuer: one elected lane runs the whole role
+    // (a warp-level wait + elect + __syncwarp per 4-MMA chunk drained the MMA queue between chunks)
+    if (elect_one()) {
     const int ksteps = p.block_k >> 4;  // UMMA_K = 16 for bf16
     uint32_t lt = 0;                    // local tile index
     int s = 0;                          // ring slot and phase
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
       for (int i = 0; i < num_chunks; ++i) {
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
-        if (elect_one()) {
+        {
           const uint32_t sa = smem_base + s * stage_bytes;
           const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + p.stage_a_bytes);
           // K steps of 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field per step
@@ -211,13 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
           umma_commit(&empty_bar[s]);                               // smem slot free once these MMAs retire
           if (i == num_chunks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        __syncwarp();
         if (++s == p.num_stages) {
           s = 0;
           ph ^= 1u;
         }
       }
     }
+    }   // elected lane
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
     const int group = (warp - 2) >> 2;   // owns accumulator stage `group`
