@@ -67,6 +67,7 @@ struct __align__(64) HaloParams {
   CUtensorMap tm_a[4];
   CUtensorMap tm_w;
   CUtensorMap tm_out;
+  CUtensorMap tm_res;        // residual panels (EXTRA 5: TMA ring in shared memory), same boxes / swizzle as tm_out
   // geometry
   int patch_mode;            // 1: 16x8 pixel patches (3x3), 0: 128 consecutive pixels (1x1)
   int hout, wout;
@@ -88,7 +89,8 @@ struct __align__(64) HaloParams {
   uint32_t tap_hi_a[9];      // upper descriptor word per tap (SBO differs between parity planes)
   uint32_t hi_b;
   uint32_t idesc, tmem_cols;
-  uint32_t off_b, off_stage;
+  uint32_t off_b, off_stage, off_res;
+  uint32_t res_tx_bytes;     // bytes of one residual panel load
   // epilogue
   const float* bias;
   const __nv_bfloat16* residual;
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
   __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t res_full_bar[4];   // residual ring: 2 slots per epilogue group
   __shared__ __align__(16) float bias_s[256];
   __shared__ uint32_t tmem_base_smem;
 
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 4);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&res_full_bar[a], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -528,8 +532,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
-    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2)), "extra operands are only combined with bf16 output");
-    static_assert(EXTRA < 3 || (OUT_F32 && !SILU), "the fused head decode consumes the f32 logits of a bare 1x1 conv");
+    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5)), "extra operands are only combined with bf16 output");
+    // EXTRA 5 = the bf16 residual of EXTRA 1, but its panels arrive through a two-slot TMA ring in shared memory (requested
+    // by the group's leader two panels ahead) instead of per-thread register loads: with 8 epilogue warps the register
+    // path keeps only ~16 KB in flight per SM and the residual read ran at ~2 TB/s next to everything else.
+    constexpr int MX = EXTRA == 5 ? 1 : EXTRA;   // arithmetic flavour of the extra operand
+    static_assert((EXTRA != 3 && EXTRA != 4) || (OUT_F32 && !SILU), "the fused head decode consumes the f32 logits of a bare 1x1 conv");
     constexpr int kPanelCols = OUT_F32 ? 32 : 64;      // a full staging panel row is 128 bytes
     constexpr int kChunks = kPanelCols / 32;           // 32-column chunks per panel
     constexpr int kWordsPerChunk = OUT_F32 ? 32 : 16;  // packed output words of one chunk
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const int sts_chunks = p.pb >> 4;       // 16-byte chunks per staging row (2, 4 or 8)
     WaitClock wc(p.prof != nullptr && leader);
     const long long role_t0 = wc.begin();
-    if constexpr (EXTRA >= 3) {
+    if constexpr (EXTRA == 3 || EXTRA == 4) {
       // ---------------------------------------------------------------- fused head decode (flat 1x1 mode only)
       // The last conv of a head tower writes no logits: this thread owns one anchor row of the accumulator and reduces it
       // on the spot -- DFL + anchor/stride decode -> NMS corners (EXTRA 3), or class max on the logits -> (score, class)
@@ -661,7 +669,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         c1 = (rem - ti * p.tiles_w) * kPatchW;
         c2 = ti * kPatchH;
         c3 = img;
-        if (EXTRA != 0) {
+        if (EXTRA == 1 || EXTRA == 2) {
           const int h = c2 + (r >> 3), w = c1 + (r & 7);
           if (h < p.hout && w < p.wout) {
             if (EXTRA == 1)
@@ -674,7 +682,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         c1 = s * 128;
         c2 = 0;
         c3 = 0;
-        if (EXTRA != 0) {
+        if (EXTRA == 1 || EXTRA == 2) {
           const long long pix = static_cast<long long>(s) * 128 + r;
           if (pix < p.mtot) {
             if (EXTRA == 1) {
@@ -697,6 +705,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     const int first_cols = min(32, p.block_n);
     uint32_t lt = 0;
     const int n_it = sched.iters();
+    // ---- residual ring (EXTRA 5): leader-side prefetch cursor over this group's panels, consumer-side panel counter
+    const uint32_t res_base = smem_base + p.off_res + group * 2 * kStageBytes;
+    const uint32_t res_bar0 = smem_u32(&res_full_bar[group * 2]);
+    int pf_it = group, pf_mt = 0, pf_pn = 0, pf_s0 = 0, pf_m = 0, pf_j = 0;
+    auto pf_issue = [&]() {   // request the cursor's panel into slot (pf_j & 1) and advance
+      if (pf_it >= n_it) return;
+      if (pf_mt == 0 && pf_pn == 0) sched.get(pf_it, pf_s0, pf_m);
+      int c1, c2, c3;
+      const void* unused;
+      locate(pf_s0 + pf_mt, c1, c2, c3, unused);
+      const int slot = pf_j & 1;
+      mbar_arrive_expect_tx(&res_full_bar[group * 2 + slot], p.res_tx_bytes);
+      tma_load_4d(&p.tm_res, &res_full_bar[group * 2 + slot], res_base + slot * kStageBytes, n0 + pf_pn * p.pc, c1, c2, c3);
+      ++pf_j;
+      if (++pf_pn == npanels) {
+        pf_pn = 0;
+        if (++pf_mt == pf_m) {
+          pf_mt = 0;
+          pf_it += 2;
+        }
+      }
+    };
+    if (EXTRA == 5 && leader) {
+      pf_issue();
+      pf_issue();
+    }
+    int rj = 0;   // panels consumed by this group
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it, ++lt) {
       if ((lt & 1) != static_cast<uint32_t>(group)) continue;
@@ -704,9 +739,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       sched.get(it, s0, m_cur);
       int nc1 = 0, nc2 = 0, nc3 = 0;
       const void* nrow = nullptr;
-      ExtraRegs<EXTRA> exn;                  // first chunk of the coming sub-tile's extra operand
+      ExtraRegs<MX> exn;                     // first chunk of the coming sub-tile's extra operand
       locate(s0, nc1, nc2, nc3, nrow);
-      if (EXTRA != 0 && nrow != nullptr) exn.load(nrow, 0, first_cols);
+      if (EXTRA != 0 && EXTRA != 5 && nrow != nullptr) exn.load(nrow, 0, first_cols);
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
       wc.end(1, tw);
@@ -717,19 +752,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         const void* ex_row = nrow;
         const bool ex_valid = ex_row != nullptr;
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
-        ExtraRegs<EXTRA> ex[kChunks];
+        ExtraRegs<MX> ex[kChunks];
         ex[0] = exn;
         bool ex0_ready = true;              // ex[0] already holds the first chunk of the coming panel
         if (mt + 1 < m_cur) {               // request the next sub-tile's first chunk a whole sub-tile ahead
           locate(s0 + mt + 1, nc1, nc2, nc3, nrow);
-          if (EXTRA != 0 && nrow != nullptr) exn.load(nrow, 0, first_cols);
+          if (EXTRA != 0 && EXTRA != 5 && nrow != nullptr) exn.load(nrow, 0, first_cols);
         }
 #pragma unroll 1
         for (int pn = 0; pn < npanels; ++pn) {
           const int col0 = pn * p.pc;
           const int ncols = min(p.pc, p.block_n - col0);
-          if (EXTRA != 0 && ex_valid && !ex0_ready) ex[0].load(ex_row, col0, min(32, ncols));
+          if (EXTRA != 0 && EXTRA != 5 && ex_valid && !ex0_ready) ex[0].load(ex_row, col0, min(32, ncols));
           ex0_ready = false;
+          uint32_t res_slot = 0;
+          if (EXTRA == 5) {                 // this panel's residual has landed in the ring
+            res_slot = res_base + (rj & 1) * kStageBytes;
+            wait_addr(res_bar0 + 8 * (rj & 1), (rj >> 1) & 1);
+            ++rj;
+          }
           uint32_t o[kChunks * kWordsPerChunk];
 #pragma unroll
           for (int ch = 0; ch < kChunks; ++ch) {
@@ -742,7 +783,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
               } else {
                 tmem_ld_32x32b_x16(taddr0 + col0 + cc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
               }
-              if (EXTRA != 0 && ex_valid) {   // issue the next chunk's extra-operand loads one chunk ahead of their use
+              if (EXTRA == 5) {               // this row's 64 bytes of the chunk from the swizzled ring slot
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (cc * 2 + i * 16 < ncols * 2) {
+                    const uint32_t off = swz(row_off + cc * 2 + i * 16, p.smask);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(ex[ch].q[i].x), "=r"(ex[ch].q[i].y), "=r"(ex[ch].q[i].z), "=r"(ex[ch].q[i].w)
+                                 : "r"(res_slot + off));
+                  }
+              }
+              if (EXTRA != 0 && EXTRA != 5 && ex_valid) {   // issue the next chunk's extra-operand loads one chunk ahead of their use
                 if (ch + 1 < kChunks) {
                   if (cc + 32 < ncols) ex[ch + 1].load(ex_row, col0 + cc + 32, min(32, ncols - cc - 32));
                 } else if (pn + 1 < npanels) {
@@ -752,9 +803,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
               }
               tmem_ld_wait();
               if (full)
-                epilogue_math<32, SILU, OUT_F32, EXTRA>(v, bias_s + col0 + cc, ex[ch], ex_valid, &o[ch * kWordsPerChunk]);
+                epilogue_math<32, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || EXTRA == 5, &o[ch * kWordsPerChunk]);
               else
-                epilogue_math<16, SILU, OUT_F32, EXTRA>(v, bias_s + col0 + cc, ex[ch], ex_valid, &o[ch * kWordsPerChunk]);
+                epilogue_math<16, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || EXTRA == 5, &o[ch * kWordsPerChunk]);
             }
           }
           if (mt == m_cur - 1 && pn == npanels - 1) {
@@ -768,6 +819,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           if (leader) bulk_wait_read_all();
           named_bar_sync(bar_id, 128);
           wc.end(2, tw);
+          if (EXTRA == 5 && leader) pf_issue();   // every thread has read this panel's ring slot: refill it (two panels ahead)
           const int nvalid16 = (ncols * (OUT_F32 ? 4 : 2)) >> 4;   // 16-byte chunks of this row that hold data
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -815,7 +867,8 @@ static uint32_t desc_hi(uint32_t sbo_bytes, int bk) {
 
 // Fills `p` for K-chunk width bk (cin_pad is fixed by the packed weights).  *fits = false when no shared-memory plan
 // exists for this bk (the caller retries with a narrower chunk).
-static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits) {
+static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits,
+                        bool res_ring = false) {
   int rc;
   *fits = true;
   memset(&p, 0, sizeof(p));
@@ -977,8 +1030,30 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     }
   }
 
+  if (res_ring) {   // residual panels: the output store's boxes and swizzle on the residual tensor
+    const CUtensorMapSwizzle swz_res =
+        p.pb >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const uint64_t rpx = static_cast<uint64_t>(d->res_pitch) * 2;
+    if (p.patch_mode) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(wout), static_cast<uint64_t>(hout),
+                                static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {rpx, rpx * wout, rpx * wout * hout};
+      const uint32_t box[4] = {static_cast<uint32_t>(p.pc), kPatchW, kPatchH, 1};
+      if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res)) != TOD_OK) return rc;
+      p.res_tx_bytes = static_cast<uint32_t>(p.pb) * kPatchW * kPatchH;
+    } else {
+      const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(mtot), 1, 1};
+      const uint64_t str[3] = {rpx, rpx * mtot, rpx * mtot};
+      const uint32_t box[4] = {static_cast<uint32_t>(p.pc), rows, 1, 1};
+      if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res)) != TOD_OK) return rc;
+      p.res_tx_bytes = static_cast<uint32_t>(p.pb) * rows;
+    }
+  }
+
   // ---- shared-memory plan: m sub-tiles per weight tile, A ring, B ring or resident weights
-  const uint32_t staging = 2 * kStageBytes;
+  // (+ four residual panels when the residual goes through the shared-memory ring; that plan needs resident weights)
+  const uint32_t staging = (res_ring ? 6 : 2) * kStageBytes;
   const uint32_t budget = kHaloSmemLimit - 1024 - staging;
   const uint32_t b_total = static_cast<uint32_t>(taps) * p.chunks * p.b_slot_bytes;
   const bool may_station = taps * p.chunks <= kMaxB && d->reserved[2] != 1;
@@ -990,7 +1065,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   double best_cost = -1.0;
   for (int m = m_max; m >= 1; --m) {
     const uint32_t a_slot = m * p.sub_bytes;
-    for (int stn = 1; stn >= 0; --stn) {
+    for (int stn = 1; stn >= (res_ring ? 1 : 0); --stn) {
       int sa, sb;
       if (stn) {
         if (!may_station || b_total + 2 * a_slot > budget) continue;
@@ -1041,7 +1116,8 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.a_slot_bytes = p.m * p.sub_bytes;
   p.off_b = p.sa * p.a_slot_bytes;
   p.off_stage = p.off_b + p.sb * p.b_slot_bytes;
-  const size_t smem = static_cast<size_t>(p.off_stage) + staging + 1024;
+  p.off_res = p.off_stage + 2 * kStageBytes;
+  const size_t smem = static_cast<size_t>(p.off_stage) + staging + 1024;   // staging includes the residual ring
   TOD_CHECK_ARG(smem <= kHaloSmemLimit, "conv: shared-memory plan overflows (%zu bytes)", smem);
   p.num_super = ceil_div(p.num_subtiles, p.m);
 
@@ -1061,9 +1137,10 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 }
 
 // kernel variants: [0..2] bf16 out, no activation, extra 0/1/2; [3..5] bf16 out, SiLU, extra 0/1/2; [6] f32 out, no
-// activation; [7] f32 out, SiLU; [8] fused box decode; [9] fused class decode
+// activation; [7] f32 out, SiLU; [8] fused box decode; [9] fused class decode; [10] bf16 out, SiLU, residual through
+// the shared-memory TMA ring
 using HaloKernel = void (*)(HaloParams);
-constexpr int kHaloVariants = 10;
+constexpr int kHaloVariants = 11;
 static HaloKernel halo_kernel(int i) {
   switch (i) {
     case 0: return conv_halo_tcgen05<false, false, 0>;
@@ -1075,7 +1152,8 @@ static HaloKernel halo_kernel(int i) {
     case 6: return conv_halo_tcgen05<false, true, 0>;
     case 7: return conv_halo_tcgen05<true, true, 0>;
     case 8: return conv_halo_tcgen05<false, true, 3>;
-    default: return conv_halo_tcgen05<false, true, 4>;
+    case 9: return conv_halo_tcgen05<false, true, 4>;
+    default: return conv_halo_tcgen05<true, false, 5>;
   }
 }
 
@@ -1113,6 +1191,11 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
   bool fits = false;
   const int bk0 = pick_block_k(d->cin, d->block_k);
   const int cin_pad = round_up(d->cin, bk0);
+  if (extra == 1 && silu && fuse == nullptr && d->reserved[2] != 1) {
+    // residual through the shared-memory TMA ring when the weights can stay resident next to it
+    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, true)) != TOD_OK) return rc;
+    if (fits) kvar = 10;
+  }
   for (int bk = bk0; bk >= 16 && !fits; bk >>= 1)
     if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits)) != TOD_OK) return rc;
   TOD_CHECK_ARG(fits, "conv: no shared-memory plan fits (cin %d cout %d ksize %d stride %d)", d->cin, d->cout, d->ksize,
