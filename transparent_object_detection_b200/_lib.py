@@ -15,7 +15,7 @@ SYMBOLS = (
     "tod_version", "tod_last_error", "tod_device_ok", "tod_conv2d_nhwc_bf16", "tod_conv_weight_layout",
     "tod_stem_conv_nchw_f32", "tod_sppf_pool_nhwc_bf16", "tod_head_decode", "tod_nms_prepare_dense",
     "tod_nms_workspace_bytes", "tod_nms", "tod_conv2d_nhwc_bf16_simt_check", "tod_decode_box_from_head",
-    "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8",
+    "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
 )
 
 

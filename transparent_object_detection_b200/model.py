@@ -243,14 +243,15 @@ def dets_to_reference_rows(dets: torch.Tensor, counts: np.ndarray, input_shape, 
     mx = int(counts.max()) if len(counts) else 0
     if mx == 0:
         return out
+    # correct_boxes is elementwise: one call on the padded (B, mx) block instead of one per image (the per-image numpy
+    # calls cost more host time per batch than the GPU needs for the whole batch), then per-image slices
     host = dets[:, :mx].cpu().numpy()
+    box_xy, box_wh = (host[..., 0:2] + host[..., 2:4]) / 2, host[..., 2:4] - host[..., 0:2]
+    with np.errstate(all="ignore"):          # rows past an image's count are stale
+        host[..., :4] = DecodeBox.correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
     for i, n in enumerate(counts):
-        if n == 0:
-            continue
-        o = host[i, :n].copy()
-        box_xy, box_wh = (o[:, 0:2] + o[:, 2:4]) / 2, o[:, 2:4] - o[:, 0:2]
-        o[:, :4] = DecodeBox.correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
-        out[i] = o
+        if n > 0:
+            out[i] = host[i, :n].copy()
     return out
 
 
