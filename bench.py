@@ -228,7 +228,10 @@ def main():
     table = []
     if rank == 0:
         x_u8 = eng.input_buffer("u8", 0)
-        eng.run_network(x_u8); eng.run_decode(False, False, True); eng.run_nms(CONF, IOU)
+        eng.run_network(x_u8, fused_decode=eng.fuse_head_decode)
+        if not eng.fuse_head_decode:
+            eng.run_decode(False, False, True)
+        eng.run_nms(CONF, IOU)
         torch.cuda.synchronize()
         import ctypes as C
         from transparent_object_detection_b200._lib import check
@@ -241,7 +244,10 @@ def main():
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 if kind == "conv":
-                    check(eng.L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
+                    if eng.fuse_head_decode and name in eng.head_fuse:      # what the captured graph runs
+                        check(eng.L.tod_conv2d_head_decode(C.byref(payload), C.byref(eng.head_fuse[name]), st), name)
+                    else:
+                        check(eng.L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
                 elif kind == "stem":
                     w, bb, out = payload
                     check(eng.L.tod_stem_conv_nhwc_u8(x_u8.data_ptr(), w.data_ptr(), bb.data_ptr(), out.ptr, B, args.size,
@@ -251,9 +257,10 @@ def main():
                     check(eng.L.tod_sppf_pool_nhwc_bf16(buf.ptr, B, buf.h, buf.w, c_, buf.pitch, st), name)
                 b.record()
                 evs.append((kind, name, payload, a, b))
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); eng.run_decode(False, False, True); b.record()
-            evs.append(("decode", "head_decode", None, a, b))
+            if not eng.fuse_head_decode:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); eng.run_decode(False, False, True); b.record()
+                evs.append(("decode", "head_decode", None, a, b))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); eng.run_nms(CONF, IOU); b.record()
             evs.append(("nms", "nms(sort+segments+compact)", None, a, b))
