@@ -15,6 +15,7 @@ device memory, streams and CUDA-graph capture only.  There is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -108,6 +109,7 @@ class DetectorEngine:
         self.conv_meta: Dict[str, dict] = {}          # fp32 weights / views per conv (tools/gpu_netcheck.py)
         self.launches_forward = 0
         self.fork_head = True          # head towers as parallel graph branches (graph_for)
+        self.prioritise_critical_path = os.environ.get("TOD_GRAPH_PRIO", "1") != "0"
         self._graph = None
         self._graphs: Dict[Tuple, "torch.cuda.CUDAGraph"] = {}   # (input kind, slot, conf, iou, head_out, decoded)
         self._inputs: Dict[Tuple[str, int], torch.Tensor] = {}   # static input buffers per (kind, slot)
@@ -351,7 +353,12 @@ class DetectorEngine:
             ready = torch.cuda.Event()
             ready.record(main)
             for tower in ("box", "cls"):
-                side = self._side_streams.setdefault((tower, lvl), torch.cuda.Stream(self.device))
+                # stream priorities become kernel-node priorities in the captured graph: the big level-0 towers are
+                # throughput work that fills gaps, the small deep-level towers are the tail of the critical path
+                if (tower, lvl) not in self._side_streams:
+                    prio = 0 if (lvl == 0 or not self.prioritise_critical_path) else -1
+                    self._side_streams[(tower, lvl)] = torch.cuda.Stream(self.device, priority=prio)
+                side = self._side_streams[(tower, lvl)]
                 side.wait_event(ready)
                 prefix = f"head.{tower}.{lvl}."
                 for k2, n2, p2 in self.ops:
@@ -435,7 +442,8 @@ class DetectorEngine:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        cap = torch.cuda.Stream(self.device, priority=-1 if self.prioritise_critical_path else 0)   # backbone + neck chain
+        with torch.cuda.graph(g, stream=cap):
             body()
         self._graphs[key] = g
         return g

@@ -116,11 +116,13 @@ class BaseModel(nn.Module):
         """Call after changing weights in place (load_state_dict does it automatically)."""
         self._engines.clear()
 
-    def engine(self, batch: int, in_h: int, in_w: int, device=None) -> DetectorEngine:
+    def engine(self, batch: int, in_h: int, in_w: int, device=None, instance: int = 0) -> DetectorEngine:
+        """instance > 0: an independent plan (own activation arena, graphs and result buffers) for the same shape, so
+        that two batches can be in flight at once (Detector.submit alternates instances 0 and 1)."""
         device = torch.device("cuda" if device is None else device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = (batch, in_h, in_w, str(device))
+        key = (batch, in_h, in_w, str(device)) if instance == 0 else (batch, in_h, in_w, str(device), instance)
         eng = self._engines.get(key)
         if eng is None:
             eng = DetectorEngine(self.state_dict(), self.num_classes, self.base_channels, self.base_depth,
@@ -261,8 +263,9 @@ class Detector:
     net -> decode_box -> non_max_suppression, captured as ONE CUDA graph per (batch, H, W, thresholds)."""
 
     def __init__(self, model: BaseModel, input_shape: Tuple[int, int], confidence: float = 0.05, nms_iou: float = 0.5,
-                 letterbox_image: bool = True, max_boxes: int = 100):
+                 letterbox_image: bool = True, max_boxes: int = 100, pipeline_depth: int = 3):
         self.model, self.input_shape = model, tuple(input_shape)
+        self.pipeline_depth = max(1, int(pipeline_depth))     # batches that may be in flight between submit and collect
         self.confidence, self.nms_iou, self.letterbox_image, self.max_boxes = confidence, nms_iou, letterbox_image, max_boxes
         self.bbox_util = DecodeBox(model.num_classes, self.input_shape)
 
@@ -297,34 +300,43 @@ class Detector:
         if (kind == "u8" and images.shape[3] != 3) or (kind == "f32" and images.shape[1] != 3):
             raise ValueError(f"bad image batch shape {tuple(images.shape)} for dtype {images.dtype}")
         dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        eng = self.model.engine(images.shape[0], self.input_shape[0], self.input_shape[1], dev)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if not hasattr(self, "_pipe"):
+            self._pipe = {}
+        pkey = (images.shape[0], str(dev))
+        st = self._pipe.get(pkey)
+        if st is None:
+            with torch.cuda.device(dev):
+                st = {"copy": torch.cuda.Stream(dev), "compute": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)], "seq": 0,
+                      "free": [None] * self.pipeline_depth}
+            self._pipe[pkey] = st
+        seq = st["seq"]
+        st["seq"] = seq + 1
+        slot = seq % self.pipeline_depth
+        # `pipeline_depth` independent plans (own activation arena, graph, result buffers) over two compute streams that
+        # consecutive batches alternate on: the tail of batch i (NMS: a few CTAs) and the first layers of batch i+1 overlap
+        # instead of serialising, while batch i+2 uploads.  A plan is reused only after its previous batch has finished.
+        eng = self.model.engine(images.shape[0], self.input_shape[0], self.input_shape[1], dev, instance=slot)
         with torch.cuda.device(eng.device):
-            if not hasattr(self, "_pipe"):
-                self._pipe = {}
-            st = self._pipe.get(id(eng))
-            if st is None:
-                st = {"copy": torch.cuda.Stream(eng.device), "compute": torch.cuda.Stream(eng.device), "next": 0,
-                      "free": [None, None]}
-                self._pipe[id(eng)] = st
-            slot = st["next"]
-            st["next"] = slot ^ 1
-            g = eng.graph_for(kind, slot, self.confidence, self.nms_iou)       # captured on first use
-            x = eng.input_buffer(kind, slot)
+            g = eng.graph_for(kind, 0, self.confidence, self.nms_iou)       # captured on first use
+            x = eng.input_buffer(kind, 0)
             caller = torch.cuda.current_stream(eng.device)
+            compute = st["compute"][seq & 1]
             with torch.cuda.stream(st["copy"]):
                 st["copy"].wait_stream(caller)                   # `images` may have been produced on the caller's stream
                 if st["free"][slot] is not None:
-                    st["copy"].wait_event(st["free"][slot])      # the previous replay that read this slot has finished
+                    st["copy"].wait_event(st["free"][slot])      # the previous replay that read this input has finished
                 x.copy_(images, non_blocking=True)
                 copied = torch.cuda.Event()
                 copied.record(st["copy"])
-            with torch.cuda.stream(st["compute"]):
-                st["compute"].wait_event(copied)
+            with torch.cuda.stream(compute):
+                compute.wait_event(copied)
                 g.replay()
                 done = torch.cuda.Event()
-                done.record(st["compute"])
+                done.record(compute)
             st["free"][slot] = done
-        return PendingBatch(eng, slot, done)
+        return PendingBatch(eng, 0, done)
 
     def collect(self, pending: "PendingBatch", image_shape=None) -> List[Optional[np.ndarray]]:
         """Wait for a submitted batch and return the reference's rows (D2H of the counts, then of the kept rows only)."""
