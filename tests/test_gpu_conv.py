@@ -45,6 +45,14 @@ CASES = [
     ("1x1_n144_f32", 1, 16, 16, 64, 144, 1, 1, {"f32": True, "act": 0}),
     ("1x1_m_not_mult_128", 3, 7, 9, 32, 32, 1, 1, {}),
     ("1x1_res_views", 2, 16, 16, 64, 64, 1, 1, {"residual": True, "out_pitch": 128, "out_off": 64}),
+    # upsample-add operand through the shared-memory ring (1x1 on 16x8 pixel tiles): ragged tiles, several panels, weights
+    # that do not stay resident, two N tiles, channel windows on both sides
+    ("1x1_upadd_ragged_40x40_n256", 2, 40, 40, 256, 256, 1, 1, {"upadd": True}),
+    ("1x1_upadd_80x80_n128_views", 1, 80, 80, 128, 128, 1, 1, {"upadd": True, "x_pitch": 192, "x_off": 64, "out_pitch": 384,
+                                                                 "out_off": 128}),
+    ("1x1_upadd_n512_two_ntiles", 1, 20, 12, 64, 512, 1, 1, {"upadd": True}),
+    ("1x1_upadd_n32_register_path", 1, 12, 12, 64, 32, 1, 1, {"upadd": True}),
+    ("1x1_upadd_noact_register_path", 1, 16, 16, 64, 64, 1, 1, {"upadd": True, "act": 0}),
 ]
 VARIANTS = {"pertap": 1, "halo": 2}
 

@@ -15,6 +15,7 @@
 using namespace tod;
 
 struct Params {
+  int row_bytes;   // 128: SWIZZLE_128B (4 K-steps per row), 64: SWIZZLE_64B (2 K-steps per row)
   int n, shift_rows, sbo_rows, iters, distinct_a;  // distinct_a: number of different A start rows cycled through
   int b_shift_rows;
   long long* cycles;  // per CTA
@@ -44,17 +45,27 @@ __global__ void __launch_bounds__(128, 1) rate(const Params p) {
   const uint32_t tmem = tmem_base_smem;
   if (warp == 1) {
     const uint32_t sa = base, sb = base + 96 * 1024;
-    const uint32_t hi_a = ((p.sbo_rows * 128u) >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t rb = p.row_bytes, lt = rb == 128 ? 2u : 4u;
+    const uint32_t hi_a = ((p.sbo_rows * rb) >> 4) | (1u << 14) | (lt << 29);
+    const uint32_t hi_b = ((8u * rb) >> 4) | (1u << 14) | (lt << 29);
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(p.n) >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_lo = umma_desc_lo(sa + p.shift_rows * 128), b_lo = umma_desc_lo(sb + p.b_shift_rows * 128);
+    const uint32_t a_lo = umma_desc_lo(sa + p.shift_rows * rb), b_lo = umma_desc_lo(sb + p.b_shift_rows * rb);
     long long t0 = 0;
     if (elect_one()) {
       t0 = clock64();
       // distinct_a views: A start moves by 3 rows per view (like conv taps); every k4 call = 4 MMAs
-      for (int it = 0; it < p.iters / 4; it += 2) {
-        umma_bf16_k4(tmem, a_lo, hi_a, b_lo, hi_b, idesc, 1);
-        umma_bf16_k4(tmem + p.n, a_lo + (p.distinct_a > 1 ? 24u : 0u), hi_a, b_lo, hi_b, idesc, 1);
+      if (rb == 128) {
+        for (int it = 0; it < p.iters / 4; it += 2) {
+          umma_bf16_k4(tmem, a_lo, hi_a, b_lo, hi_b, idesc, 1);
+          umma_bf16_k4(tmem + p.n, a_lo + (p.distinct_a > 1 ? 24u : 0u), hi_a, b_lo, hi_b, idesc, 1);
+        }
+      } else {   // 64-byte rows: 2 K-steps per row, four accumulators in turn like the conv's m = 4 sub-tiles
+        for (int it = 0; it < p.iters / 2; it += 4) {
+          umma_bf16_k2(tmem, a_lo, hi_a, b_lo, hi_b, idesc, 1);
+          umma_bf16_k2(tmem + p.n, a_lo + 768u, hi_a, b_lo, hi_b, idesc, 1);
+          umma_bf16_k2(tmem + 2 * p.n, a_lo + 1536u, hi_a, b_lo, hi_b, idesc, 1);
+          umma_bf16_k2(tmem + 3 * p.n, a_lo + 2304u, hi_a, b_lo, hi_b, idesc, 1);
+        }
       }
       umma_commit(&bar);
     }
@@ -79,7 +90,7 @@ int main() {
   cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   std::vector<long long> hc(sms);
   const int iters = 4096;
-  struct Cfg { int n, shift, sbo, da, bshift; const char* name; };
+  struct Cfg { int n, shift, sbo, da, bshift; const char* name; int rb = 128; };
   const Cfg cfgs[] = {
       {256, 0, 8, 1, 0, "N256 aligned sbo8"},   {256, 1, 8, 1, 0, "N256 shift1 sbo8"},   {256, 0, 10, 1, 0, "N256 aligned sbo10"},
       {256, 11, 10, 1, 0, "N256 shift11 sbo10"}, {256, 0, 16, 1, 0, "N256 aligned sbo16"}, {256, 1, 16, 1, 0, "N256 shift1 sbo16"},
@@ -88,9 +99,12 @@ int main() {
       {64, 0, 8, 1, 0, "N64 aligned sbo8"},     {64, 11, 10, 1, 0, "N64 shift11 sbo10"},
       {32, 0, 8, 1, 0, "N32 aligned sbo8"},     {32, 11, 10, 1, 0, "N32 shift11 sbo10"},
       {16, 0, 8, 1, 0, "N16 aligned sbo8"},
+      {32, 0, 8, 1, 0, "N32 64B rows aligned sbo8", 64},   {32, 11, 10, 1, 0, "N32 64B rows shift11 sbo10", 64},
+      {64, 0, 8, 1, 0, "N64 64B rows aligned sbo8", 64},   {64, 11, 10, 1, 0, "N64 64B rows shift11 sbo10", 64},
+      {128, 11, 10, 1, 0, "N128 64B rows shift11 sbo10", 64},
   };
   for (const Cfg& c : cfgs) {
-    Params p{c.n, c.shift, c.sbo, iters, c.da, c.bshift, dc};
+    Params p{c.rb, c.n, c.shift, c.sbo, iters, c.da, c.bshift, dc};
     for (int rep = 0; rep < 2; ++rep) {
       rate<<<sms, 128, smem>>>(p);
       cudaError_t e = cudaDeviceSynchronize();

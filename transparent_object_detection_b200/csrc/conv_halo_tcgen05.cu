@@ -417,14 +417,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     // which the 8-deep MMA queue (<= 512 tensor cycles at N = 128) drained: the tensor pipe was busy 66 % on the
     // weight-streaming layers.
     if (elect_one()) {
+    WaitClock wc(p.prof != nullptr);
+    const long long role_t0 = wc.begin();
+    // The whole role is instantiated per K-step count (4 / 2 / generic) and the sub-tile loop is unrolled (m <= 4): at
+    // N <= 64 one MMA is <= 48 tensor cycles and the ~25 uniform-datapath instructions (constant reloads, three K-step
+    // branch tests, loop control) that the rolled version spent per 2-MMA call made the issuing thread the limiter
+    // (measured with tools/conv_profile.py: the role was busy issuing 92 % of a 32->32 3x3 layer at ~85 cycles per MMA
+    // against the 40-cycle tensor floor of profiles/r1_probe_umma_rate.txt).
+    auto run = [&](auto ksc) {
+    constexpr int KS = decltype(ksc)::value;
     uint32_t lt = 0;
     int ai = 0, rbi = 0;
     uint32_t pha = 0, phb = 0;
     const uint32_t sub16 = p.sub_bytes >> 4;
     const uint32_t b_ring = smem_base + p.off_b;
-    const bool ks4 = p.ksteps == 4, ks2 = p.ksteps == 2;
-    WaitClock wc(p.prof != nullptr);
-    const long long role_t0 = wc.begin();
+    const uint32_t hi_b = p.hi_b, idesc = p.idesc, block_n = p.block_n;
     const int n_it = sched.iters();
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it, ++lt) {
@@ -443,8 +450,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         // One synchronisation group = taps [T0, T0 + GSZ) of this chunk: an overlapped wait for the group's weight tiles
         // (and the A slot at the start of a chunk), then GSZ * m * ksteps MMAs back to back.  T0 / GSZ are compile-time
         // so that the per-tap descriptor offsets are constant-bank operands (statically indexed kernel parameters); read
-        // through a runtime tap index they were dependent ~50-cycle loads in front of every tap, and with N <= 64
-        // (<= 48 tensor cycles per MMA) the issuing thread, not the tensor pipe, was the limiter.
+        // through a runtime tap index they were dependent ~50-cycle loads in front of every tap.
         auto group = [&](auto t0c, auto gszc) {
           constexpr int T0 = decltype(t0c)::value, GSZ = decltype(gszc)::value;
           // (the host makes the ring size a multiple of the group size, so a group's slots are consecutive and share a phase)
@@ -474,36 +480,36 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           if (mask != 0) wait_set(bars, pars, mask);
           wc.end(3, tw2);
           tcgen05_fence_after();
-          {
+          uint32_t b_lo = umma_desc_lo(b_ring + slot0 * p.b_slot_bytes);
+          const uint32_t b_step = p.b_slot_bytes >> 4;
 #pragma unroll
-            for (int j = 0; j < GSZ; ++j) {
-              constexpr int dummy = 0;
-              (void)dummy;
-              const int t = T0 + j;                                   // compile-time after unrolling
-              const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
-              const uint32_t hi_a = p.tap_hi_a[t];
-              const uint32_t b_lo = umma_desc_lo(b_ring + (slot0 + j) * p.b_slot_bytes);
-              const uint32_t accf = (c | t) != 0 ? 1u : 0u;
-#pragma unroll 1
-              for (int mt = 0; mt < m_cur; ++mt) {
-                const uint32_t d_t = tmem_acc + mt * p.block_n;
+          for (int j = 0; j < GSZ; ++j) {
+            const int t = T0 + j;                                   // compile-time after unrolling
+            const uint32_t a_lo = umma_desc_lo(a_base + p.tap_a_off[t]);
+            const uint32_t hi_a = p.tap_hi_a[t];
+            const uint32_t accf = (c | t) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              if (mt < m_cur) {
+                const uint32_t d_t = tmem_acc + mt * block_n;
                 const uint32_t al = a_lo + mt * sub16;
-                if (ks4) {
-                  umma_bf16_k4(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
-                } else if (ks2) {   // 32-channel chunks
-                  umma_bf16_k2(d_t, al, hi_a, b_lo, p.hi_b, p.idesc, accf);
+                if (KS == 4) {
+                  umma_bf16_k4(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
+                } else if (KS == 2) {   // 32-channel chunks
+                  umma_bf16_k2(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
                 } else {
 #pragma unroll 1
                   for (int k = 0; k < p.ksteps; ++k)
-                    umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, p.hi_b, p.idesc, accf | (k != 0 ? 1u : 0u));
+                    umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, hi_b, idesc, accf | (k != 0 ? 1u : 0u));
                 }
               }
-              if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
             }
-            if (T0 + GSZ >= p.num_taps) {
-              umma_commit(&a_empty[ai]);
-              if (c == p.chunks - 1) umma_commit(&tmem_full_bar[acc]);
-            }
+            if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
+            b_lo += b_step;
+          }
+          if (T0 + GSZ >= p.num_taps) {
+            umma_commit(&a_empty[ai]);
+            if (c == p.chunks - 1) umma_commit(&tmem_full_bar[acc]);
           }
         };
         using std::integral_constant;
@@ -524,6 +530,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         }
       }
     }
+    };   // run
+    if (p.ksteps == 4) run(std::integral_constant<int, 4>{});
+    else if (p.ksteps == 2) run(std::integral_constant<int, 2>{});
+    else run(std::integral_constant<int, 0>{});
     if (wc.on) {
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
@@ -532,11 +542,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
-    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5)), "extra operands are only combined with bf16 output");
+    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5 || EXTRA == 6)), "extra operands are only combined with bf16 output");
     // EXTRA 5 = the bf16 residual of EXTRA 1, but its panels arrive through a two-slot TMA ring in shared memory (requested
     // by the group's leader two panels ahead) instead of per-thread register loads: with 8 epilogue warps the register
     // path keeps only ~16 KB in flight per SM and the residual read ran at ~2 TB/s next to everything else.
-    constexpr int MX = EXTRA == 5 ? 1 : EXTRA;   // arithmetic flavour of the extra operand
+    // EXTRA 6 = the f32 upsample-add of EXTRA 2 through the same ring (1x1 conv run on 16x8 pixel tiles): a panel's operand
+    // is the 8x4 low-resolution pixels under the tile, two [32 px x 32 f32] SWIZZLE_128B boxes, and the thread of output
+    // pixel (y, x) reads low-resolution row (y/2)*4 + x/2.  The register path issued 8 LDG.128 per 32 columns per thread
+    // whose lanes hit 16 different 512-byte-apart rows; the epilogue, not HBM, bounded those layers (MMA role waited for
+    // a free accumulator 77 % of the kernel).
+    constexpr int MX = EXTRA == 5 ? 1 : (EXTRA == 6 ? 2 : EXTRA);   // arithmetic flavour of the extra operand
+    constexpr bool RING = EXTRA == 5 || EXTRA == 6;
     static_assert((EXTRA != 3 && EXTRA != 4) || (OUT_F32 && !SILU), "the fused head decode consumes the f32 logits of a bare 1x1 conv");
     constexpr int kPanelCols = OUT_F32 ? 32 : 64;      // a full staging panel row is 128 bytes
     constexpr int kChunks = kPanelCols / 32;           // 32-column chunks per panel
@@ -717,7 +733,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       locate(pf_s0 + pf_mt, c1, c2, c3, unused);
       const int slot = pf_j & 1;
       mbar_arrive_expect_tx(&res_full_bar[group * 2 + slot], p.res_tx_bytes);
-      tma_load_4d(&p.tm_res, &res_full_bar[group * 2 + slot], res_base + slot * kStageBytes, n0 + pf_pn * p.pc, c1, c2, c3);
+      if (EXTRA == 6) {
+        tma_load_4d(&p.tm_res, &res_full_bar[group * 2 + slot], res_base + slot * kStageBytes, n0 + pf_pn * p.pc, c1 >> 1, c2 >> 1, c3);
+        tma_load_4d(&p.tm_res, &res_full_bar[group * 2 + slot], res_base + slot * kStageBytes + 4096, n0 + pf_pn * p.pc + 32,
+                    c1 >> 1, c2 >> 1, c3);
+      } else {
+        tma_load_4d(&p.tm_res, &res_full_bar[group * 2 + slot], res_base + slot * kStageBytes, n0 + pf_pn * p.pc, c1, c2, c3);
+      }
       ++pf_j;
       if (++pf_pn == npanels) {
         pf_pn = 0;
@@ -727,10 +749,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         }
       }
     };
-    if (EXTRA == 5 && leader) {
+    if (RING && leader) {
       pf_issue();
       pf_issue();
     }
+    const uint32_t lr_off = static_cast<uint32_t>(((r >> 4) << 2) + ((r & 7) >> 1)) * 128u;   // EXTRA 6: this row's low-res row
     int rj = 0;   // panels consumed by this group
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it, ++lt) {
@@ -741,7 +764,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       const void* nrow = nullptr;
       ExtraRegs<MX> exn;                     // first chunk of the coming sub-tile's extra operand
       locate(s0, nc1, nc2, nc3, nrow);
-      if (EXTRA != 0 && EXTRA != 5 && nrow != nullptr) exn.load(nrow, 0, first_cols);
+      if (EXTRA != 0 && !RING && nrow != nullptr) exn.load(nrow, 0, first_cols);
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
       wc.end(1, tw);
@@ -757,16 +780,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
         bool ex0_ready = true;              // ex[0] already holds the first chunk of the coming panel
         if (mt + 1 < m_cur) {               // request the next sub-tile's first chunk a whole sub-tile ahead
           locate(s0 + mt + 1, nc1, nc2, nc3, nrow);
-          if (EXTRA != 0 && EXTRA != 5 && nrow != nullptr) exn.load(nrow, 0, first_cols);
+          if (EXTRA != 0 && !RING && nrow != nullptr) exn.load(nrow, 0, first_cols);
         }
 #pragma unroll 1
         for (int pn = 0; pn < npanels; ++pn) {
           const int col0 = pn * p.pc;
           const int ncols = min(p.pc, p.block_n - col0);
-          if (EXTRA != 0 && EXTRA != 5 && ex_valid && !ex0_ready) ex[0].load(ex_row, col0, min(32, ncols));
+          if (EXTRA != 0 && !RING && ex_valid && !ex0_ready) ex[0].load(ex_row, col0, min(32, ncols));
           ex0_ready = false;
           uint32_t res_slot = 0;
-          if (EXTRA == 5) {                 // this panel's residual has landed in the ring
+          if (RING) {                       // this panel's residual / upsample-add operand has landed in the ring
             res_slot = res_base + (rj & 1) * kStageBytes;
             wait_addr(res_bar0 + 8 * (rj & 1), (rj >> 1) & 1);
             ++rj;
@@ -793,7 +816,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
                                  : "r"(res_slot + off));
                   }
               }
-              if (EXTRA != 0 && EXTRA != 5 && ex_valid) {   // issue the next chunk's extra-operand loads one chunk ahead of their use
+              if (EXTRA == 6) {               // 128 bytes (32 f32) of this row's low-resolution pixel from the chunk's box
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const uint32_t off = swz(lr_off + i * 16, 7u);
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(ex[ch].q[i].x), "=r"(ex[ch].q[i].y), "=r"(ex[ch].q[i].z), "=r"(ex[ch].q[i].w)
+                               : "r"(res_slot + ch * 4096 + off));
+                }
+              }
+              if (EXTRA != 0 && !RING && ex_valid) {   // issue the next chunk's extra-operand loads one chunk ahead of their use
                 if (ch + 1 < kChunks) {
                   if (cc + 32 < ncols) ex[ch + 1].load(ex_row, col0 + cc + 32, min(32, ncols - cc - 32));
                 } else if (pn + 1 < npanels) {
@@ -803,9 +835,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
               }
               tmem_ld_wait();
               if (full)
-                epilogue_math<32, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || EXTRA == 5, &o[ch * kWordsPerChunk]);
+                epilogue_math<32, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || RING, &o[ch * kWordsPerChunk]);
               else
-                epilogue_math<16, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || EXTRA == 5, &o[ch * kWordsPerChunk]);
+                epilogue_math<16, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || RING, &o[ch * kWordsPerChunk]);
             }
           }
           if (mt == m_cur - 1 && pn == npanels - 1) {
@@ -819,7 +851,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           if (leader) bulk_wait_read_all();
           named_bar_sync(bar_id, 128);
           wc.end(2, tw);
-          if (EXTRA == 5 && leader) pf_issue();   // every thread has read this panel's ring slot: refill it (two panels ahead)
+          if (RING && leader) pf_issue();   // every thread has read this panel's ring slot: refill it (two panels ahead)
           const int nvalid16 = (ncols * (OUT_F32 ? 4 : 2)) >> 4;   // 16-byte chunks of this row that hold data
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -867,8 +899,10 @@ static uint32_t desc_hi(uint32_t sbo_bytes, int bk) {
 
 // Fills `p` for K-chunk width bk (cin_pad is fixed by the packed weights).  *fits = false when no shared-memory plan
 // exists for this bk (the caller retries with a narrower chunk).
+// res_ring: 0 none, 1 bf16 residual panels, 2 f32 upsample-add panels (1x1 conv on 16x8 pixel tiles) through the
+// shared-memory TMA ring of the epilogue groups.
 static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits,
-                        bool res_ring = false) {
+                        int res_ring = 0) {
   int rc;
   *fits = true;
   memset(&p, 0, sizeof(p));
@@ -899,7 +933,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   TOD_CHECK_ARG(mtot < (1ll << 31), "conv: too many output pixels");
   // ---- A operand: tensor maps, loads per (sub-tile, chunk), per-tap descriptor views
   uint32_t sub_bytes = 0;
-  if (d->ksize == 1) {
+  if (d->ksize == 1 && res_ring != 2) {
     p.patch_mode = 0;
     const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
     const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(mtot), 1, 1};
@@ -922,7 +956,19 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     const long long nsub = static_cast<long long>(d->batch) * p.tiles_per_img;
     TOD_CHECK_ARG(nsub < (1ll << 30), "conv: too many tiles");
     p.num_subtiles = static_cast<int>(nsub);
-    if (d->stride == 1) {
+    if (d->ksize == 1) {   // 1x1 on pixel tiles (no halo): one box = 128 rows in the canonical 8-row-group layout
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
+                                static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
+      const uint32_t box[4] = {static_cast<uint32_t>(bk), kPatchW, kPatchH, 1};
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+      p.n_aloads = 1;
+      p.al_map[0] = 0;
+      p.a_tx_bytes = 128 * rb;
+      p.tap_a_off[0] = 0;
+      p.tap_hi_a[0] = desc_hi(8 * rb, bk);
+      sub_bytes = 128 * rb;
+    } else if (d->stride == 1) {
       const int pw = kPatchW + 2, ph = kPatchH + 2;
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
                                 static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
@@ -1030,7 +1076,21 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     }
   }
 
-  if (res_ring) {   // residual panels: the output store's boxes and swizzle on the residual tensor
+  if (res_ring == 2) {   // low-resolution f32 operand: [32 f32 x 4 x 8 px] boxes, two per 64-column panel
+    if (p.pc != 64 || !p.patch_mode || (hout & 1) || (wout & 1)) {
+      *fits = false;
+      return TOD_OK;
+    }
+    const uint64_t upx = static_cast<uint64_t>(d->cout) * 4;
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(wout / 2), static_cast<uint64_t>(hout / 2),
+                              static_cast<uint64_t>(d->batch)};
+    const uint64_t str[3] = {upx, upx * (wout / 2), upx * (wout / 2) * (hout / 2)};
+    const uint32_t box[4] = {32, kPatchW / 2, kPatchH / 2, 1};
+    if ((rc = encode_map(&p.tm_res, d->d_upadd, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) !=
+        TOD_OK)
+      return rc;
+    p.res_tx_bytes = 2u * 4096u;
+  } else if (res_ring) {   // residual panels: the output store's boxes and swizzle on the residual tensor
     const CUtensorMapSwizzle swz_res =
         p.pb >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     const uint64_t rpx = static_cast<uint64_t>(d->res_pitch) * 2;
@@ -1065,7 +1125,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   double best_cost = -1.0;
   for (int m = m_max; m >= 1; --m) {
     const uint32_t a_slot = m * p.sub_bytes;
-    for (int stn = 1; stn >= (res_ring ? 1 : 0); --stn) {
+    for (int stn = 1; stn >= (res_ring == 1 ? 1 : 0); --stn) {
       int sa, sb;
       if (stn) {
         if (!may_station || b_total + 2 * a_slot > budget) continue;
@@ -1138,9 +1198,9 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 
 // kernel variants: [0..2] bf16 out, no activation, extra 0/1/2; [3..5] bf16 out, SiLU, extra 0/1/2; [6] f32 out, no
 // activation; [7] f32 out, SiLU; [8] fused box decode; [9] fused class decode; [10] bf16 out, SiLU, residual through
-// the shared-memory TMA ring
+// the shared-memory TMA ring; [11] bf16 out, SiLU, upsample-add through the ring
 using HaloKernel = void (*)(HaloParams);
-constexpr int kHaloVariants = 11;
+constexpr int kHaloVariants = 12;
 static HaloKernel halo_kernel(int i) {
   switch (i) {
     case 0: return conv_halo_tcgen05<false, false, 0>;
@@ -1153,7 +1213,8 @@ static HaloKernel halo_kernel(int i) {
     case 7: return conv_halo_tcgen05<true, true, 0>;
     case 8: return conv_halo_tcgen05<false, true, 3>;
     case 9: return conv_halo_tcgen05<false, true, 4>;
-    default: return conv_halo_tcgen05<true, false, 5>;
+    case 10: return conv_halo_tcgen05<true, false, 5>;
+    default: return conv_halo_tcgen05<true, false, 6>;
   }
 }
 
@@ -1193,8 +1254,13 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
   const int cin_pad = round_up(d->cin, bk0);
   if (extra == 1 && silu && fuse == nullptr && d->reserved[2] != 1) {
     // residual through the shared-memory TMA ring when the weights can stay resident next to it
-    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, true)) != TOD_OK) return rc;
+    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 1)) != TOD_OK) return rc;
     if (fits) kvar = 10;
+  }
+  if (extra == 2 && silu && fuse == nullptr && d->ksize == 1 && d->stride == 1 && d->cout % 64 == 0 && d->reserved[2] != 1) {
+    // upsample-add operand through the ring (1x1 conv on pixel tiles)
+    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 2)) != TOD_OK) return rc;
+    if (fits) kvar = 11;
   }
   for (int bk = bk0; bk >= 16 && !fits; bk >>= 1)
     if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits)) != TOD_OK) return rc;
