@@ -791,7 +791,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           uint32_t res_slot = 0;
           if (RING) {                       // this panel's residual / upsample-add operand has landed in the ring
             res_slot = res_base + (rj & 1) * kStageBytes;
+            tw = wc.begin();
             wait_addr(res_bar0 + 8 * (rj & 1), (rj >> 1) & 1);
+            wc.end(3, tw);   // (tools) ring waits are reported together with the staging-written barrier
             ++rj;
           }
           uint32_t o[kChunks * kWordsPerChunk];
