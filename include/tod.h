@@ -205,6 +205,38 @@ int tod_nms(const float* d_cand_box, const float* d_cand_conf, const int32_t* d_
             void* d_work, int64_t work_bytes,
             int32_t* d_keep_idx, int32_t* d_keep_count, float* d_dets, void* stream);
 
+/*
+ * Letterbox preprocessing on the device.
+ * Replaces: resize_image  utils/utils.py:16-30 (Pillow Image.resize(size, Image.BICUBIC) + Image.new((128,128,128)) +
+ *           paste at ((w-nw)//2, (h-nh)//2)) as called by utils/callbacks.py:142-143 and dataset/coco/get_map.py:57-59;
+ *           the /255 of preprocess_input (utils/utils.py:65-67) is folded into the stem weights (tod_stem_conv_nhwc_u8).
+ * Pillow's 8-bit resampler is integer arithmetic, so the canvas is reproduced bit for bit.
+ *
+ * tod_resample_coeffs_bicubic (HOST function, no CUDA): windows and 22-bit fixed-point weights of one axis, Pillow
+ *   Resample.c precompute_coeffs + normalize_coeffs_8bpc with the bicubic filter (a = -0.5), full-image box.
+ *   With h_bounds == NULL or h_coef == NULL only *ksize is written (size query).
+ *     h_bounds i32 [out_size, 2] = (first input index, tap count); h_coef i32 [out_size, ksize] (unused taps 0).
+ * tod_letterbox_bicubic_u8: n same-sized uint8 HWC RGB images -> n (dst_h, dst_w, 3) canvases: horizontal pass
+ *   (src_w -> new_w, into d_tmp [n, src_h, new_w, 3]), vertical pass (src_h -> new_h) written at (off_y, off_x) of the
+ *   canvas, pad_value everywhere else.  A pass whose size does not change is skipped, like Pillow's.
+ *   d_xbounds/d_xcoef/xksize: tod_resample_coeffs_bicubic(src_w, new_w) copied to the device; d_y*: (src_h, new_h).
+ */
+typedef struct tod_letterbox_desc {
+  const uint8_t* d_src;
+  uint8_t* d_tmp;
+  uint8_t* d_dst;
+  int64_t src_image_stride, dst_image_stride; /* bytes between consecutive images */
+  int32_t n, src_h, src_w, dst_h, dst_w, new_h, new_w, off_y, off_x, pad_value;
+  const int32_t* d_xbounds;
+  const int32_t* d_xcoef;
+  const int32_t* d_ybounds;
+  const int32_t* d_ycoef;
+  int32_t xksize, yksize;
+  int32_t reserved[4];
+} tod_letterbox_desc;
+int tod_resample_coeffs_bicubic(int32_t in_size, int32_t out_size, int32_t* h_bounds, int32_t* h_coef, int32_t* ksize);
+int tod_letterbox_bicubic_u8(const tod_letterbox_desc* desc, void* stream);
+
 /* Debug/verification helper used by tests only: direct (non-tensor-core) evaluation of the same conv
  * descriptor on CUDA cores, fp32 accumulate.  Never called by the product path. */
 int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* desc, void* stream);

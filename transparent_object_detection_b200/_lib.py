@@ -16,6 +16,7 @@ SYMBOLS = (
     "tod_stem_conv_nchw_f32", "tod_sppf_pool_nhwc_bf16", "tod_head_decode", "tod_nms_prepare_dense",
     "tod_nms_workspace_bytes", "tod_nms", "tod_conv2d_nhwc_bf16_simt_check", "tod_decode_box_from_head",
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
+    "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8",
 )
 
 
@@ -46,6 +47,18 @@ class HeadFuseDesc(C.Structure):
         ("mode", C.c_int32), ("nc", C.c_int32), ("level_off", C.c_int32), ("anchors", C.c_int32),
         ("in_h", C.c_int32), ("in_w", C.c_int32), ("stride", C.c_float),
         ("d_cand_box", C.c_void_p), ("d_cand_conf", C.c_void_p), ("d_cand_cls", C.c_void_p),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+class LetterboxDesc(C.Structure):
+    _fields_ = [
+        ("d_src", C.c_void_p), ("d_tmp", C.c_void_p), ("d_dst", C.c_void_p),
+        ("src_image_stride", C.c_int64), ("dst_image_stride", C.c_int64),
+        ("n", C.c_int32), ("src_h", C.c_int32), ("src_w", C.c_int32), ("dst_h", C.c_int32), ("dst_w", C.c_int32),
+        ("new_h", C.c_int32), ("new_w", C.c_int32), ("off_y", C.c_int32), ("off_x", C.c_int32), ("pad_value", C.c_int32),
+        ("d_xbounds", C.c_void_p), ("d_xcoef", C.c_void_p), ("d_ybounds", C.c_void_p), ("d_ycoef", C.c_void_p),
+        ("xksize", C.c_int32), ("yksize", C.c_int32),
         ("reserved", C.c_int32 * 4),
     ]
 
@@ -92,6 +105,8 @@ def lib() -> C.CDLL:
     L.tod_decode_box_from_head.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p]
     L.tod_debug_set_conv_profile.argtypes = [C.c_void_p]
+    L.tod_resample_coeffs_bicubic.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)  # fail loudly if the binary is stale
     _lib = L

@@ -20,6 +20,7 @@ SOURCES = {
     "stem_conv.cu": [],
     "stem_u8_tcgen05.cu": [],
     "sppf_pool.cu": [],
+    "letterbox.cu": [],
     "head_decode.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],
 }

@@ -249,8 +249,15 @@ def dets_to_reference_rows(dets: torch.Tensor, counts: np.ndarray, input_shape, 
     # calls cost more host time per batch than the GPU needs for the whole batch), then per-image slices
     host = dets[:, :mx].cpu().numpy()
     box_xy, box_wh = (host[..., 0:2] + host[..., 2:4]) / 2, host[..., 2:4] - host[..., 0:2]
+    shapes = np.asarray(image_shape)
     with np.errstate(all="ignore"):          # rows past an image's count are stale
-        host[..., :4] = DecodeBox.correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+        if shapes.ndim == 2:                 # one (h, w) per image: the letterbox geometry differs per image
+            if shapes.shape[0] != len(counts):
+                raise ValueError(f"{shapes.shape[0]} image shapes for {len(counts)} images")
+            for i in range(len(counts)):
+                host[i, :, :4] = DecodeBox.correct_boxes(box_xy[i], box_wh[i], input_shape, shapes[i], letterbox_image)
+        else:
+            host[..., :4] = DecodeBox.correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
     for i, n in enumerate(counts):
         if n > 0:
             out[i] = host[i, :n].copy()
@@ -265,6 +272,7 @@ class Detector:
     def __init__(self, model: BaseModel, input_shape: Tuple[int, int], confidence: float = 0.05, nms_iou: float = 0.5,
                  letterbox_image: bool = True, max_boxes: int = 100, pipeline_depth: int = 3):
         self.model, self.input_shape = model, tuple(input_shape)
+        self.gpu_letterbox = True            # detect_image_rows / detect_images letterbox on the device
         self.pipeline_depth = max(1, int(pipeline_depth))     # batches that may be in flight between submit and collect
         self.confidence, self.nms_iou, self.letterbox_image, self.max_boxes = confidence, nms_iou, letterbox_image, max_boxes
         self.bbox_util = DecodeBox(model.num_classes, self.input_shape)
@@ -300,11 +308,52 @@ class Detector:
         if (kind == "u8" and images.shape[3] != 3) or (kind == "f32" and images.shape[1] != 3):
             raise ValueError(f"bad image batch shape {tuple(images.shape)} for dtype {images.dtype}")
         dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        return self._submit(images.shape[0], dev, kind, lambda x: x.copy_(images, non_blocking=True))
+
+    def submit_images(self, images: Sequence, device=None) -> "PendingBatch":
+        """Raw RGB images of any sizes ((h, w, 3) uint8 arrays / tensors or PIL images) -> letterbox ON THE DEVICE
+        (csrc/letterbox.cu, bit-exact with the reference's Pillow BICUBIC resize_image, utils/utils.py:16-30) straight
+        into the network's uint8 input batch -> the same graph replay as submit().  collect() un-letterboxes every
+        image with its own shape (remembered in the handle)."""
+        from .preprocess import Letterbox
+        arrs = []
+        for im in images:
+            if isinstance(im, torch.Tensor):
+                t = im
+            else:
+                if hasattr(im, "mode"):                       # PIL image: cvtColor (utils/utils.py:9-14)
+                    im = im if im.mode == "RGB" else im.convert("RGB")
+                t = torch.from_numpy(np.ascontiguousarray(np.asarray(im, dtype=np.uint8)))
+            if t.dim() != 3 or t.shape[2] != 3 or t.dtype != torch.uint8:
+                raise ValueError(f"images must be (h, w, 3) uint8, got {t.dtype} {tuple(t.shape)}")
+            arrs.append(t)
+        if not arrs:
+            raise ValueError("no images")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if not hasattr(self, "_letterbox"):
+            self._letterbox = Letterbox(self.input_shape, self.letterbox_image)
+
+        def fill(x):
+            i = 0
+            while i < len(arrs):                              # runs of equal-sized images go through one launch
+                j = i + 1
+                while j < len(arrs) and arrs[j].shape == arrs[i].shape:
+                    j += 1
+                src = arrs[i].unsqueeze(0) if j == i + 1 else torch.stack([a.to(x.device, non_blocking=True) for a in arrs[i:j]])
+                self._letterbox(src, x[i:j])
+                i = j
+
+        pend = self._submit(len(arrs), dev, "u8", fill)
+        pend.image_shapes = np.array([[a.shape[0], a.shape[1]] for a in arrs])
+        return pend
+
+    def _submit(self, batch: int, dev, kind: str, fill) -> "PendingBatch":
+        """One pipeline step: `fill(x)` populates the plan's static input x on the copy stream, then the graph replays."""
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         if not hasattr(self, "_pipe"):
             self._pipe = {}
-        pkey = (images.shape[0], str(dev))
+        pkey = (batch, str(dev))
         st = self._pipe.get(pkey)
         if st is None:
             with torch.cuda.device(dev):
@@ -317,7 +366,7 @@ class Detector:
         # `pipeline_depth` independent plans (own activation arena, graph, result buffers) over two compute streams that
         # consecutive batches alternate on: the tail of batch i (NMS: a few CTAs) and the first layers of batch i+1 overlap
         # instead of serialising, while batch i+2 uploads.  A plan is reused only after its previous batch has finished.
-        eng = self.model.engine(images.shape[0], self.input_shape[0], self.input_shape[1], dev, instance=slot)
+        eng = self.model.engine(batch, self.input_shape[0], self.input_shape[1], dev, instance=slot)
         with torch.cuda.device(eng.device):
             g = eng.graph_for(kind, 0, self.confidence, self.nms_iou)       # captured on first use
             x = eng.input_buffer(kind, 0)
@@ -327,7 +376,7 @@ class Detector:
                 st["copy"].wait_stream(caller)                   # `images` may have been produced on the caller's stream
                 if st["free"][slot] is not None:
                     st["copy"].wait_event(st["free"][slot])      # the previous replay that read this input has finished
-                x.copy_(images, non_blocking=True)
+                fill(x)
                 copied = torch.cuda.Event()
                 copied.record(st["copy"])
             with torch.cuda.stream(compute):
@@ -344,22 +393,31 @@ class Detector:
         pending.done.synchronize()
         cnt, dets = eng.slot_outputs(pending.slot)
         counts = cnt.cpu().numpy()
-        shape = image_shape if image_shape is not None else self.input_shape
+        shape = image_shape if image_shape is not None else getattr(pending, "image_shapes", None)
+        if shape is None:
+            shape = self.input_shape
         rows = dets_to_reference_rows(dets, counts, self.input_shape, shape, self.letterbox_image)
         pending.d2h_bytes = counts.nbytes + int(counts.max() if len(counts) else 0) * counts.shape[0] * 24
         return rows
 
     def detect_image_rows(self, image) -> Optional[np.ndarray]:
-        """One PIL image / (H, W, 3) uint8 array -> the reference's (n, 6) rows or None.  Letterbox on the host (PIL
-        BICUBIC like utils/utils.py:16-30); the uint8 pixels go to the GPU as they are (/255 is fused into the stem)."""
+        """One PIL image / (H, W, 3) uint8 array -> the reference's (n, 6) rows or None.  The raw pixels go to the GPU as
+        they are; the letterbox (utils/utils.py:16-30, bit-exact with Pillow BICUBIC) runs there and /255 is fused into
+        the stem (gpu_letterbox=False: Pillow on the host, the reference's own call)."""
         from PIL import Image
         if not isinstance(image, Image.Image):
             image = Image.fromarray(np.asarray(image))
+        if self.gpu_letterbox:
+            return self.collect(self.submit_images([image]))[0]
         image_shape = np.array(np.shape(image)[0:2])
         image = image if image.mode == "RGB" else image.convert("RGB")
         image_data = _letterbox(image, (self.input_shape[1], self.input_shape[0]), self.letterbox_image)
         x = torch.from_numpy(np.ascontiguousarray(np.asarray(image_data, dtype=np.uint8))[None])
         return self.detect(x, image_shape)[0]
+
+    def detect_images(self, images: Sequence) -> List[Optional[np.ndarray]]:
+        """A batch of raw RGB images of any sizes -> the reference's rows per image (device letterbox + network + NMS)."""
+        return self.collect(self.submit_images(images))
 
     def detect_image(self, image_id, image, results: list, clsid2catid) -> list:
         """reference mAP_FOCUS.detect_image (dataset/coco/get_map.py:37-96): `image` is a PIL image or an
@@ -389,6 +447,7 @@ class PendingBatch:
 
     def __init__(self, engine: DetectorEngine, slot: int, done: "torch.cuda.Event"):
         self.engine, self.slot, self.done, self.d2h_bytes = engine, slot, done, 0
+        self.image_shapes = None          # per-image (h, w) when the batch came through submit_images
 
 
 def _letterbox(image, size, letterbox_image):
