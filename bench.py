@@ -224,7 +224,7 @@ def main():
     t0 = time.perf_counter()
     inflight = []
     for i in range(args.steps):
-        inflight.append(det.submit(hosts[i & 1]))
+        inflight.append(det.submit(hosts[i & 1], (args.size, args.size)))   # shapes at submit: rows un-letterboxed on the device
         if len(inflight) == det.pipeline_depth:
             pend = inflight.pop(0)
             det.collect(pend)

@@ -206,6 +206,19 @@ int tod_nms(const float* d_cand_box, const float* d_cand_conf, const int32_t* d_
             int32_t* d_keep_idx, int32_t* d_keep_count, float* d_dets, void* stream);
 
 /*
+ * Un-letterbox the kept rows on the device.
+ * Replaces: the tail of non_max_suppression  utils/bbox_utils.py:176-180 + correct_boxes :84-117 (numpy on the host in
+ *           the reference), same dtype flow (float32 centres/sizes, float64 letterbox arithmetic, float32 rows).
+ *   d_dets f32 [batch, anchors, 6] rows [x1, y1, x2, y2, conf, cls] (tod_nms), first d_keep_count[b] valid per image
+ *   d_params f64 [batch, 6] = offset_y, offset_x, scale_y, scale_x, image_h, image_w per image, where
+ *            new = round(image * min(input / image)), offset = (input - new) / 2 / input, scale = input / new (:105-107)
+ *            (offset 0, scale 1 when letterbox == 0)
+ *   d_rows  f32 [batch, anchors, 6] rows [y1, x1, y2, x2, conf, cls] in image pixels (may alias d_dets)
+ */
+int tod_correct_boxes(const float* d_dets, const int32_t* d_keep_count, int32_t batch, int32_t anchors,
+                      const double* d_params, int32_t letterbox, float* d_rows, void* stream);
+
+/*
  * Letterbox preprocessing on the device.
  * Replaces: resize_image  utils/utils.py:16-30 (Pillow Image.resize(size, Image.BICUBIC) + Image.new((128,128,128)) +
  *           paste at ((w-nw)//2, (h-nh)//2)) as called by utils/callbacks.py:142-143 and dataset/coco/get_map.py:57-59;

@@ -408,3 +408,58 @@ def test_detector_uint8_pipeline_matches_float_path_and_is_order_safe():
     o_f = eng.head_out
     assert float((o_u8[:, :4] - o_f[:, :4]).abs().max()) <= 1.5
     assert float((o_u8[:, 4:] - o_f[:, 4:]).abs().max()) <= 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ f3: device correct_boxes
+@pytest.mark.parametrize("letterbox", [True, False])
+def test_correct_boxes_device_bit_exact_vs_numpy_flow(letterbox):
+    """tod_correct_boxes against the numpy dtype flow of utils/bbox_utils.py:84-117,176-180 (host port pinned to the
+    reference fixture in tests/test_host_cpu.py): random kept rows, one (h, w) per image, bit-exact float32 rows."""
+    import ctypes as C
+    from transparent_object_detection_b200 import DecodeBox, lib
+    from transparent_object_detection_b200._lib import check
+    from transparent_object_detection_b200.model import box_correction_params
+    g = torch.Generator().manual_seed(11)
+    B, A = 5, 300
+    xy = torch.rand((B, A, 2), generator=g)
+    wh = torch.rand((B, A, 2), generator=g) * 0.5
+    dets = torch.cat([xy - wh / 2, xy + wh / 2, torch.rand((B, A, 1), generator=g),
+                      torch.randint(0, 80, (B, A, 1), generator=g).float()], 2).contiguous()
+    counts = torch.tensor([300, 0, 17, 1, 250], dtype=torch.int32)
+    shapes = np.array([[480, 640], [640, 480], [1080, 1920], [333, 777], [640, 640]])
+    input_shape = (640, 640)
+    prm = torch.from_numpy(box_correction_params(input_shape, shapes, B, letterbox)).cuda()
+    d_dev, c_dev = dets.cuda(), counts.cuda()
+    out = torch.full_like(d_dev, -7.0)
+    check(lib().tod_correct_boxes(d_dev.data_ptr(), c_dev.data_ptr(), B, A, prm.data_ptr(), int(letterbox), out.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "tod_correct_boxes")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    host = dets.numpy().copy()
+    for i in range(B):
+        n = int(counts[i])
+        rows = host[i, :n].copy()
+        if n:
+            box_xy, box_wh = (rows[:, 0:2] + rows[:, 2:4]) / 2, rows[:, 2:4] - rows[:, 0:2]
+            rows[:, :4] = DecodeBox.correct_boxes(box_xy, box_wh, input_shape, shapes[i], letterbox)
+        assert np.array_equal(got[i, :n], rows), i
+        assert np.all(got[i, n:] == -7.0)                      # rows past the count are not touched
+
+
+def test_detector_device_corrected_rows_equal_host_corrected_rows():
+    import transparent_object_detection_b200 as T
+    from oracle import synth
+    C_, d, m = synth.SCALES["n"]
+    model = T.BaseModel(80, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    x = torch.from_numpy(synth.make_images_u8(3, 64, 96, seed=9))
+    shapes = np.array([[48, 96], [200, 150], [64, 96]])
+    for lb in (True, False):
+        det = T.Detector(model, (64, 96), confidence=0.01, nms_iou=0.5, letterbox_image=lb)
+        dev_rows = det.detect(x, shapes)                        # shapes known at submit: tod_correct_boxes
+        host_rows = det.collect(det.submit(x), shapes)          # shapes given at collect: numpy on the host
+        assert sum(r is not None for r in host_rows) > 0
+        for a, b in zip(dev_rows, host_rows):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert np.array_equal(a, b)

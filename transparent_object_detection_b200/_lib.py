@@ -16,7 +16,7 @@ SYMBOLS = (
     "tod_stem_conv_nchw_f32", "tod_sppf_pool_nhwc_bf16", "tod_head_decode", "tod_nms_prepare_dense",
     "tod_nms_workspace_bytes", "tod_nms", "tod_conv2d_nhwc_bf16_simt_check", "tod_decode_box_from_head",
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
-    "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8",
+    "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes",
 )
 
 
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.tod_debug_set_conv_profile.argtypes = [C.c_void_p]
     L.tod_resample_coeffs_bicubic.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]
+    L.tod_correct_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)  # fail loudly if the binary is stale
     _lib = L

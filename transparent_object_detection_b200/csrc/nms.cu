@@ -378,6 +378,48 @@ __global__ void __launch_bounds__(kSegWarps * 32) nms_segment_kernel(const float
 }
 
 // ------------------------------------------------------------------------------------------------
+// correct_boxes (utils/bbox_utils.py:84-117) on the kept rows, in numpy's dtype flow (this file is compiled with
+// -fmad=false): centres / sizes in float32 ((x1+x2)/2, x2-x1, :179); with letterbox the centre goes to float64
+// ((yx - offset) * scale) while the size is scaled in float64 and stored back to float32 (`box_hw *= scale` is in place on
+// a float32 view); mins / maxes in float64, times the image shape, stored as float32.  Without letterbox everything
+// stays float32 and only the final in-place `boxes *= image_shape` passes through float64.
+// params [B][6] f64: offset_y, offset_x, scale_y, scale_x, image_h, image_w (computed on the host with the reference's
+// own expressions).  rows [x1, y1, x2, y2, conf, cls] -> [y1, x1, y2, x2, conf, cls] in image pixels.
+__global__ void __launch_bounds__(128) correct_boxes_kernel(const float* __restrict__ dets, const int* __restrict__ keep_count,
+                                                            int anchors, const double* __restrict__ params, int letterbox,
+                                                            float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int n = keep_count[b];
+  const double* q = params + b * 6;
+  const double off[2] = {q[0], q[1]}, sc[2] = {q[2], q[3]}, dim[2] = {q[4], q[5]};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* d = dets + (static_cast<size_t>(b) * anchors + i) * 6;
+    float* o = out + (static_cast<size_t>(b) * anchors + i) * 6;
+    const float x1 = d[0], y1 = d[1], x2 = d[2], y2 = d[3];
+    const float c32[2] = {(y1 + y2) / 2.0f, (x1 + x2) / 2.0f};    // box_yx
+    const float s32[2] = {y2 - y1, x2 - x1};                      // box_hw
+    float r[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (letterbox) {
+        const double c = (static_cast<double>(c32[a]) - off[a]) * sc[a];
+        const float hw = static_cast<float>(static_cast<double>(s32[a]) * sc[a]);
+        const double half = static_cast<double>(hw / 2.0f);
+        r[a] = static_cast<float>((c - half) * dim[a]);
+        r[a + 2] = static_cast<float>((c + half) * dim[a]);
+      } else {
+        const float half = s32[a] / 2.0f;
+        r[a] = static_cast<float>(static_cast<double>(c32[a] - half) * dim[a]);
+        r[a + 2] = static_cast<float>(static_cast<double>(c32[a] + half) * dim[a]);
+      }
+    }
+    const float conf = d[4], cls = d[5];
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+    o[4] = conf; o[5] = cls;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nms_compact_kernel(const float4* __restrict__ cand_box,
                                                           const float* __restrict__ cand_conf,
                                                           const int* __restrict__ cand_cls, int anchors, NmsWork wk,
@@ -481,5 +523,15 @@ extern "C" int tod_nms(const float* d_cand_box, const float* d_cand_conf, const 
   nms_compact_kernel<<<batch, 256, 0, st>>>(reinterpret_cast<const float4*>(d_cand_box), d_cand_conf, d_cand_cls, anchors,
                                             wk, d_keep_idx, d_keep_count, d_dets);
   TOD_CHECK_LAUNCH("nms_compact_kernel launch");
+  return TOD_OK;
+}
+
+extern "C" int tod_correct_boxes(const float* d_dets, const int32_t* d_keep_count, int32_t batch, int32_t anchors,
+                                 const double* d_params, int32_t letterbox, float* d_rows, void* stream) {
+  TOD_CHECK_ARG(d_dets != nullptr && d_keep_count != nullptr && d_params != nullptr && d_rows != nullptr, "correct_boxes: null pointer");
+  TOD_CHECK_ARG(batch > 0 && batch <= 65535 && anchors > 0, "correct_boxes: bad sizes");
+  correct_boxes_kernel<<<dim3(4, batch), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dets, d_keep_count, anchors, d_params,
+                                                                                      letterbox, d_rows);
+  TOD_CHECK_LAUNCH("correct_boxes_kernel launch");
   return TOD_OK;
 }

@@ -111,6 +111,7 @@ class DetectorEngine:
         self.fork_head = True          # head towers as parallel graph branches (graph_for)
         self.prioritise_critical_path = os.environ.get("TOD_GRAPH_PRIO", "1") != "0"
         self._graph = None
+        self._box_params = None
         self._graphs: Dict[Tuple, "torch.cuda.CUDAGraph"] = {}   # (input kind, slot, conf, iou, head_out, decoded)
         self._inputs: Dict[Tuple[str, int], torch.Tensor] = {}   # static input buffers per (kind, slot)
         self._slot_out: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -417,10 +418,19 @@ class DetectorEngine:
     def replay(self) -> None:
         self._graph.replay()
 
-    def graph_for(self, kind: str, slot: int, conf_thres: float, nms_thres: float):
-        """CUDA graph of network + decode + NMS (+ copy of the results into the slot's buffers) on the static input
-        (kind, slot); captured on first use."""
-        key = (kind, slot, float(conf_thres), float(nms_thres))
+    def box_params(self) -> torch.Tensor:
+        """(B, 6) float64 device buffer read by tod_correct_boxes in the `corrected` graphs: per image
+        offset_y, offset_x, scale_y, scale_x, image_h, image_w (model.py:box_correction_params)."""
+        if self._box_params is None:
+            self._box_params = torch.zeros((self.batch, 6), dtype=torch.float64, device=self.device)
+            self._box_params[:, 2:4] = 1.0
+        return self._box_params
+
+    def graph_for(self, kind: str, slot: int, conf_thres: float, nms_thres: float, corrected: int = -1):
+        """CUDA graph of network + decode + NMS (+ the results into the slot's buffers) on the static input
+        (kind, slot); captured on first use.  corrected = 0 / 1: the slot's rows are un-letterboxed on the device
+        (tod_correct_boxes with letterbox off / on, parameters in box_params()); -1: raw NMS rows [x1, y1, x2, y2, ..]."""
+        key = (kind, slot, float(conf_thres), float(nms_thres), int(corrected))
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -433,7 +443,12 @@ class DetectorEngine:
                 self.run_decode(False, False, True)
             self.run_nms(conf_thres, nms_thres)
             cnt.copy_(self.keep_count)
-            dets.copy_(self.dets)
+            if corrected >= 0:
+                check(self.L.tod_correct_boxes(self.dets.data_ptr(), self.keep_count.data_ptr(), self.batch, self.anchors,
+                                               self.box_params().data_ptr(), int(corrected), dets.data_ptr(), self._stream()),
+                      "tod_correct_boxes")
+            else:
+                dets.copy_(self.dets)
 
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))

@@ -238,6 +238,28 @@ class DecodeBox:
         return dets_to_reference_rows(dets, counts, input_shape, image_shape, letterbox_image)
 
 
+def box_correction_params(input_shape, image_shapes, batch: int, letterbox_image: bool) -> np.ndarray:
+    """Per-image scalars of correct_boxes (utils/bbox_utils.py:101-107), evaluated with the reference's own numpy
+    expressions -> (batch, 6) float64: offset_y, offset_x, scale_y, scale_x, image_h, image_w (tod_correct_boxes)."""
+    shapes = np.asarray(image_shapes)
+    if shapes.ndim == 1:
+        shapes = np.broadcast_to(shapes, (batch, 2))
+    if shapes.shape != (batch, 2):
+        raise ValueError(f"image shapes {shapes.shape} for a batch of {batch}")
+    out = np.zeros((batch, 6), np.float64)
+    inp = np.array(input_shape)
+    for i in range(batch):
+        image_shape = np.array(shapes[i])
+        if letterbox_image:
+            new_shape = np.round(image_shape * np.min(inp / image_shape))
+            out[i, 0:2] = (inp - new_shape) / 2.0 / inp
+            out[i, 2:4] = inp / new_shape
+        else:
+            out[i, 2:4] = 1.0
+        out[i, 4:6] = image_shape
+    return out
+
+
 def dets_to_reference_rows(dets: torch.Tensor, counts: np.ndarray, input_shape, image_shape, letterbox_image,
                            empty_is_none: bool = True) -> List[Optional[np.ndarray]]:
     """Device detections -> the reference's per-image numpy rows (utils/bbox_utils.py:176-180)."""
@@ -297,18 +319,21 @@ class Detector:
     def detect(self, images: torch.Tensor, image_shape=None) -> List[Optional[np.ndarray]]:
         """-> list of None | float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] like non_max_suppression.
         images: float32 (B, 3, H, W) in [0, 1] (the reference's tensor) or uint8 (B, H, W, 3) letterboxed RGB."""
-        return self.collect(self.submit(images), image_shape)
+        return self.collect(self.submit(images, image_shape if image_shape is not None else self.input_shape))
 
     # -- pipelined form: submit batch i+1 before collecting batch i and the upload overlaps the previous replay ---------
-    def submit(self, images: torch.Tensor) -> "PendingBatch":
-        """Enqueue upload (copy stream) -> graph replay (compute stream) of one batch and return at once."""
+    def submit(self, images: torch.Tensor, image_shape=None) -> "PendingBatch":
+        """Enqueue upload (copy stream) -> graph replay (compute stream) of one batch and return at once.
+        image_shape: (h, w) of the original images, or one (h, w) per image; when given, the kept rows are un-letterboxed
+        on the device (tod_correct_boxes) and collect() only slices them; otherwise collect(pending, image_shape) does
+        it on the host like the reference (utils/bbox_utils.py:176-180)."""
         if images.dim() != 4 or images.dtype not in (torch.float32, torch.uint8):
             raise ValueError("images must be float32 (B, 3, H, W) or uint8 (B, H, W, 3)")
         kind = "u8" if images.dtype == torch.uint8 else "f32"
         if (kind == "u8" and images.shape[3] != 3) or (kind == "f32" and images.shape[1] != 3):
             raise ValueError(f"bad image batch shape {tuple(images.shape)} for dtype {images.dtype}")
         dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        return self._submit(images.shape[0], dev, kind, lambda x: x.copy_(images, non_blocking=True))
+        return self._submit(images.shape[0], dev, kind, lambda x: x.copy_(images, non_blocking=True), image_shape)
 
     def submit_images(self, images: Sequence, device=None) -> "PendingBatch":
         """Raw RGB images of any sizes ((h, w, 3) uint8 arrays / tensors or PIL images) -> letterbox ON THE DEVICE
@@ -323,7 +348,7 @@ class Detector:
             else:
                 if hasattr(im, "mode"):                       # PIL image: cvtColor (utils/utils.py:9-14)
                     im = im if im.mode == "RGB" else im.convert("RGB")
-                t = torch.from_numpy(np.ascontiguousarray(np.asarray(im, dtype=np.uint8)))
+                t = torch.from_numpy(np.array(im, dtype=np.uint8))       # (a copy: PIL exposes read-only memory)
             if t.dim() != 3 or t.shape[2] != 3 or t.dtype != torch.uint8:
                 raise ValueError(f"images must be (h, w, 3) uint8, got {t.dtype} {tuple(t.shape)}")
             arrs.append(t)
@@ -343,11 +368,9 @@ class Detector:
                 self._letterbox(src, x[i:j])
                 i = j
 
-        pend = self._submit(len(arrs), dev, "u8", fill)
-        pend.image_shapes = np.array([[a.shape[0], a.shape[1]] for a in arrs])
-        return pend
+        return self._submit(len(arrs), dev, "u8", fill, np.array([[a.shape[0], a.shape[1]] for a in arrs]))
 
-    def _submit(self, batch: int, dev, kind: str, fill) -> "PendingBatch":
+    def _submit(self, batch: int, dev, kind: str, fill, image_shapes=None) -> "PendingBatch":
         """One pipeline step: `fill(x)` populates the plan's static input x on the copy stream, then the graph replays."""
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -368,7 +391,8 @@ class Detector:
         # instead of serialising, while batch i+2 uploads.  A plan is reused only after its previous batch has finished.
         eng = self.model.engine(batch, self.input_shape[0], self.input_shape[1], dev, instance=slot)
         with torch.cuda.device(eng.device):
-            g = eng.graph_for(kind, 0, self.confidence, self.nms_iou)       # captured on first use
+            corrected = -1 if image_shapes is None else int(bool(self.letterbox_image))
+            g = eng.graph_for(kind, 0, self.confidence, self.nms_iou, corrected)       # captured on first use
             x = eng.input_buffer(kind, 0)
             caller = torch.cuda.current_stream(eng.device)
             compute = st["compute"][seq & 1]
@@ -377,6 +401,9 @@ class Detector:
                 if st["free"][slot] is not None:
                     st["copy"].wait_event(st["free"][slot])      # the previous replay that read this input has finished
                 fill(x)
+                if image_shapes is not None:
+                    prm = torch.from_numpy(box_correction_params(self.input_shape, image_shapes, batch, self.letterbox_image))
+                    eng.box_params().copy_(prm.pin_memory(), non_blocking=True)
                 copied = torch.cuda.Event()
                 copied.record(st["copy"])
             with torch.cuda.stream(compute):
@@ -385,7 +412,9 @@ class Detector:
                 done = torch.cuda.Event()
                 done.record(compute)
             st["free"][slot] = done
-        return PendingBatch(eng, 0, done)
+        pend = PendingBatch(eng, 0, done)
+        pend.corrected = image_shapes is not None
+        return pend
 
     def collect(self, pending: "PendingBatch", image_shape=None) -> List[Optional[np.ndarray]]:
         """Wait for a submitted batch and return the reference's rows (D2H of the counts, then of the kept rows only)."""
@@ -393,10 +422,19 @@ class Detector:
         pending.done.synchronize()
         cnt, dets = eng.slot_outputs(pending.slot)
         counts = cnt.cpu().numpy()
-        shape = image_shape if image_shape is not None else getattr(pending, "image_shapes", None)
-        if shape is None:
-            shape = self.input_shape
-        rows = dets_to_reference_rows(dets, counts, self.input_shape, shape, self.letterbox_image)
+        if pending.corrected:                  # rows were un-letterboxed on the device: slice only
+            if image_shape is not None:
+                raise ValueError("this batch was submitted with its image shapes; collect() takes none")
+            rows: List[Optional[np.ndarray]] = [None] * len(counts)
+            mx = int(counts.max()) if len(counts) else 0
+            if mx > 0:
+                host = dets[:, :mx].cpu().numpy()
+                for i, n in enumerate(counts):
+                    if n > 0:
+                        rows[i] = host[i, :n].copy()
+        else:
+            shape = image_shape if image_shape is not None else self.input_shape
+            rows = dets_to_reference_rows(dets, counts, self.input_shape, shape, self.letterbox_image)
         pending.d2h_bytes = counts.nbytes + int(counts.max() if len(counts) else 0) * counts.shape[0] * 24
         return rows
 
@@ -447,7 +485,7 @@ class PendingBatch:
 
     def __init__(self, engine: DetectorEngine, slot: int, done: "torch.cuda.Event"):
         self.engine, self.slot, self.done, self.d2h_bytes = engine, slot, done, 0
-        self.image_shapes = None          # per-image (h, w) when the batch came through submit_images
+        self.corrected = False            # rows already un-letterboxed on the device (submit got the image shapes)
 
 
 def _letterbox(image, size, letterbox_image):
