@@ -13,7 +13,7 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$TAG.l
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed \
     --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"
-python tools/profile_ops.py --ops head.cls.0.0,backbone.dark4.1.m.0.cv1,backbone.dark2.1.cv1 > gpurun_out/plain_ops_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "regex:^conv_" -s 64 -c 3 -f -o gpurun_out/prof_$TAG \
-    python tools/profile_ops.py --ops head.cls.0.0,backbone.dark4.1.m.0.cv1,backbone.dark2.1.cv1 > gpurun_out/ncu_full_$TAG.log 2>&1
+python tools/profile_ops.py --ops head.cls.0.0,backbone.dark4.1.m.0.cv1,backbone.dark2.1.cv1,backbone.dark2.1.m.0.cv1,neck.h2.cv1 > gpurun_out/plain_ops_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k "regex:^conv_" -s 64 -c 5 -f -o gpurun_out/prof_$TAG \
+    python tools/profile_ops.py --ops head.cls.0.0,backbone.dark4.1.m.0.cv1,backbone.dark2.1.cv1,backbone.dark2.1.m.0.cv1,neck.h2.cv1 > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
