@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--ref-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plans", type=int, default=2, help="independent plans / streams alternating in the device-resident leg")
     ap.add_argument("--depth", type=int, default=4, help="batches in flight in the end-to-end leg (Detector.pipeline_depth)")
     ap.add_argument("--breakdown", default="", help="write the per-op eager timing table to this JSON file")
     args = ap.parse_args()
@@ -173,13 +174,14 @@ def main():
     hosts = [torch.from_numpy(synth.make_images_u8(B, args.size, args.size, seed=3 + 17 * rank + j)).pin_memory() for j in range(2)]
     # two independent plans (own activation arena + graph) on two streams, replayed alternately: consecutive batches
     # overlap the NMS tail of one with the stem / first layers of the next -- the same pipelining Detector.submit uses
-    engs = [model.engine(B, args.size, args.size, dev, instance=i) for i in range(2)]
+    NP = max(1, args.plans)
+    engs = [model.engine(B, args.size, args.size, dev, instance=i) for i in range(NP)]
     eng = engs[0]
     graphs = [e.graph_for("u8", 0, CONF, IOU) for e in engs]
     for j, e in enumerate(engs):
-        e.input_buffer("u8", 0).copy_(hosts[j])
+        e.input_buffer("u8", 0).copy_(hosts[j & 1])
     torch.cuda.synchronize()
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(NP)]
 
     def barrier():
         if world > 1:
@@ -191,8 +193,8 @@ def main():
         for st_ in streams:
             st_.wait_stream(main)
         for k in range(n):
-            with torch.cuda.stream(streams[k & 1]):
-                graphs[k & 1].replay()
+            with torch.cuda.stream(streams[k % NP]):
+                graphs[k % NP].replay()
         for st_ in streams:
             main.wait_stream(st_)
 
@@ -337,7 +339,7 @@ def main():
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"scale {args.scale} detector (BaseModel(80,{C_},{d},{m})), batch {B} per GPU, {args.size}x{args.size}, "
                                        f"nc 80, conf {CONF} iou {IOU}, random-init weights, uint8 NHWC images (/255 fused into the stem)",
-                           "timing": "CUDA events around K graph replays, two independent plans alternating on two streams (batch i's NMS tail "
+                           "timing": f"CUDA events around K graph replays, {NP} independent plans alternating on {NP} streams (batch i's NMS tail "
                                      "overlaps batch i+1's first layers); activations per pass (~2.5 GB) exceed L2 (126 MB)",
                            "single_pass_latency_ms": pass_latency_ms},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(hosts[0].numel()), "d2h_bytes_per_step": int(d2h),

@@ -463,3 +463,48 @@ def test_detector_device_corrected_rows_equal_host_corrected_rows():
             assert (a is None) == (b is None)
             if a is not None:
                 assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs 3 and 4
+def test_sharded_image_ranges_equal_the_single_batch_result():
+    """BASELINE config 3 on one GPU: the rank partition of a batch (shard_range, W = 2 and 4), each shard run as its own
+    batch, concatenated in rank order == the one-batch result, row for row (every op is per-image)."""
+    import transparent_object_detection_b200 as T
+    from oracle import synth
+    C_, d, m = synth.SCALES["n"]
+    model = T.BaseModel(80, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    x = torch.from_numpy(synth.make_images_u8(12, 160, 160, seed=4))
+    det = T.Detector(model, (160, 160), confidence=0.01, nms_iou=0.5)
+    whole = det.detect(x)
+    assert sum(r is not None for r in whole) > 0
+    for world in (2, 4):
+        parts = []
+        for rank in range(world):
+            lo, hi = T.shard_range(12, rank, world)
+            parts.extend(det.detect(x[lo:hi].contiguous()))
+        assert_dets_equal(parts, whole)
+
+
+def test_network_1280_config4_against_live_oracle():
+    """BASELINE config 4 geometry (1280x1280: A = 33600, SPPF planes 40x40) at scale n, one image, against the CPU
+    oracle evaluated in the test: boxes <= 1.5 px, scores <= 8e-3; NMS on OUR decoded tensor bit-exact with the oracle's."""
+    from oracle import detector_oracle as O, synth
+    from transparent_object_detection_b200 import BaseModel, DecodeBox
+    C_, d, m = synth.SCALES["n"]
+    sd = synth.make_state_dict(80, C_, d, m, seed=0)
+    model = BaseModel(80, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    x = torch.from_numpy(synth.make_images(1, 1280, 1280, seed=5))
+    out = model(x.cuda())
+    with torch.no_grad():
+        want = O.forward(sd, x, 80, d)
+    o = out.cpu()
+    assert tuple(o.shape) == (1, 84, 33600)
+    assert float((o[:, :4] - want[:, :4]).abs().max()) <= 1.5
+    assert float((o[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+    db = DecodeBox(80, (1280, 1280))
+    dec = db.decode_box(out)
+    want_rows = O.non_max_suppression(dec.cpu().numpy().copy(), 80, (1280, 1280), (720, 1280), True, 0.01, 0.5)
+    got_rows = db.non_max_suppression(dec, 80, (1280, 1280), np.array((720, 1280)), True, conf_thres=0.01, nms_thres=0.5)
+    assert_dets_equal(got_rows, want_rows)
