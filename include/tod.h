@@ -230,7 +230,7 @@ int tod_correct_boxes(const float* d_dets, const int32_t* d_keep_count, int32_t 
  *   With h_bounds == NULL or h_coef == NULL only *ksize is written (size query).
  *     h_bounds i32 [out_size, 2] = (first input index, tap count); h_coef i32 [out_size, ksize] (unused taps 0).
  * tod_letterbox_bicubic_u8: n same-sized uint8 HWC RGB images -> n (dst_h, dst_w, 3) canvases: horizontal pass
- *   (src_w -> new_w, into d_tmp [n, src_h, new_w, 3]), vertical pass (src_h -> new_h) written at (off_y, off_x) of the
+ *   (src_w -> new_w, into d_tmp: n * src_h * dst_w * 3 bytes, 4-byte aligned), vertical pass (src_h -> new_h) written at (off_y, off_x) of the
  *   canvas, pad_value everywhere else.  A pass whose size does not change is skipped, like Pillow's.
  *   d_xbounds/d_xcoef/xksize: tod_resample_coeffs_bicubic(src_w, new_w) copied to the device; d_y*: (src_h, new_h).
  */

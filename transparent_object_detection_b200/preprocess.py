@@ -75,7 +75,7 @@ class Letterbox:
         n, ih, iw, _ = src.shape
         pl = self._plan(ih, iw, dev)
         need_h = pl["nw"] != iw
-        tmp = torch.empty((n, ih, pl["nw"], 3), dtype=torch.uint8, device=dev) if need_h else None
+        tmp = torch.empty((n, ih, W, 3), dtype=torch.uint8, device=dev) if need_h else None   # canvas-width rows (tod.h)
         d = LetterboxDesc()
         d.d_src, d.d_dst = src.data_ptr(), out.data_ptr()
         d.d_tmp = tmp.data_ptr() if tmp is not None else None
