@@ -42,6 +42,31 @@ def conv_bn_silu(sd, prefix: str, x: torch.Tensor, stride: int = 1) -> torch.Ten
     return F.silu(y)
 
 
+def conv_bn_silu_bf16(sd, prefix: str, x: torch.Tensor, stride: int = 1) -> torch.Tensor:
+    """The same op with the build's rounding points: BN folded into the weights (fold_bn), weights
+    and input activations rounded to bf16, fp32 accumulation + fp32 bias + SiLU, output rounded to bf16.  Used by the
+    tests to separate the deviation that bf16 storage itself causes on a given random-init network from kernel error."""
+    bf = lambda t: t.to(torch.bfloat16).float()
+    w, b = fold_bn(sd, prefix)
+    y = F.conv2d(bf(x), bf(w), None, stride=stride, padding=w.shape[-1] // 2) + b.view(1, -1, 1, 1)
+    return bf(F.silu(y))
+
+
+class bf16_emulation:
+    """with bf16_emulation(): every Conv of backbone / neck / head towers evaluates through conv_bn_silu_bf16."""
+
+    def __enter__(self):
+        global conv_bn_silu
+        self._saved = conv_bn_silu
+        conv_bn_silu = conv_bn_silu_bf16
+        return self
+
+    def __exit__(self, *exc):
+        global conv_bn_silu
+        conv_bn_silu = self._saved
+        return False
+
+
 def fold_bn(sd, prefix: str) -> Tuple[torch.Tensor, torch.Tensor]:
     """reference fuse_conv, model/blocks.py:179-185: W' = diag(g/sqrt(eps+var)) W, b' = beta - g*mean/sqrt(var+eps)."""
     w = _t(sd, prefix + ".conv.weight")
