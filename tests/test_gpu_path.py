@@ -517,7 +517,7 @@ def test_every_scale_against_live_oracle(scale):
     (boxes <= 1.5 px, scores <= 8e-3).  The deeper random-init networks amplify any perturbation (activations reach
     |x| ~ 100 at scale l), so that bf16 STORAGE alone -- the fp32 oracle re-evaluated with the build's rounding points,
     oracle.bf16_emulation -- already deviates from fp32 by up to 15 px / 0.11 in score there; for those the kernel must
-    stay within 2.5x that inherent deviation on the raw head maps, and within 2 % of abs-max on every stage feature."""
+    stay within 2.5x that inherent deviation on the raw head maps, and within 4 % of abs-max on every stage feature."""
     from oracle import detector_oracle as O, synth
     from transparent_object_detection_b200 import BaseModel
     C_, d, m = synth.SCALES[scale]
