@@ -166,6 +166,28 @@ def test_decode_candidates_only_path_equals_full_path_on_adversarial_logits(nc):
         cls0[0, :, 0, 6] = float("-inf"); cls0[0, 1, 0, 6] = -90.0
         cls0[0, :, 0, 7] = 3.0; cls0[0, nc // 2, 0, 7] = float("inf")
         cls0[1, :, 1, :] = torch.randint(-2, 3, (nc, 20), generator=g).float()            # many exact ties
+        # sweep around the tie window (1e-4 below logit 2, 0.01 up to 8, 2.0 above): best logit m, runner-up m - gap, the
+        # runner-up alternately in a lower / higher class; gaps from one float32 step to just outside the window
+        ms = [-79.0, -40.0, -12.0, -5.0, -1.0, 0.0, 1.0, 1.99, 2.01, 4.0, 7.9, 8.1, 11.0, 14.9]
+        gaps = [0.0, 1.0, 3.0, 5e-5, 0.99e-4, 1.01e-4, 2e-4, 9e-3, 1.1e-2, 1.9, 2.1]      # 1.0 / 3.0 = that many ulps of m
+        k = 0
+        for m_ in ms:
+            for gp in gaps:
+                yy, xx = 2 + k // 20, k % 20
+                if yy >= 12:
+                    break
+                mt = torch.tensor(m_, dtype=torch.float32)
+                if gp in (1.0, 3.0):
+                    lo = mt.clone()
+                    for _ in range(int(gp)):
+                        lo = torch.nextafter(lo, torch.tensor(-float("inf")))
+                else:
+                    lo = mt - gp
+                cls0[1, :, yy, xx] = m_ - 3.0
+                a, b = (1, nc - 1) if k % 2 == 0 else (nc - 1, 1)
+                cls0[1, a, yy, xx] = mt
+                cls0[1, b, yy, xx] = lo
+                k += 1
     full = _run_decode(raw, nc, 96, 160, full=True)
     fast = _run_decode(raw, nc, 96, 160, full=False)
     for k in ("box", "conf", "cls"):

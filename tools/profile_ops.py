@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--ops", default="all")
     ap.add_argument("--nms", action="store_true")
     ap.add_argument("--decode", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="run the head's last convs with the fused decode epilogue")
     a = ap.parse_args()
     C_, d, m = synth.SCALES[a.scale]
     model = BaseModel(80, C_, d, m).eval()
@@ -38,7 +39,10 @@ def main():
         if want is not None and name not in want:
             continue
         if kind == "conv":
-            check(eng.L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
+            if a.fused and name in eng.head_fuse:
+                check(eng.L.tod_conv2d_head_decode(C.byref(payload), C.byref(eng.head_fuse[name]), st), name)
+            else:
+                check(eng.L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
         elif kind == "stem":
             w, b, out = payload
             check(eng.L.tod_stem_conv_nchw_f32(eng.x_static.data_ptr(), w.data_ptr(), b.data_ptr(), out.ptr, a.batch, a.size, a.size,

@@ -75,10 +75,14 @@ struct LogitTop2 {
     x1 = take ? o.x1 : x1;
   }
 };
-// ... and the logit threshold below which a class cannot tie the best float32 score: two logits can only share a score
-// when they are this close (d sigmoid / dx = s (1 - s)); outside (-80, 15) the sigmoid saturates: every class counts.
+// ... and the logit threshold below which a class cannot tie (or, through rounding, overtake) the best float32 score.
+// d sigmoid / dx = s (1 - s): a logit gap dx changes the score by dx (1 - s) relative, i.e. dx (1 - s) / 6e-8 ulps, against
+// <= ~4 ulps of evaluation error per score (expf 2 ulp, add and divide 0.5 ulp each).  m <= 2 (1 - s >= 0.12): 1e-4 is
+// 200 ulps; m <= 8 (1 - s >= 3.3e-4): 0.01 is 55 ulps; m < 15 (1 - s >= 3e-7): 2.0; outside (-80, 15) the sigmoid
+// saturates and every class counts.  (The window decides only WHICH anchors take the exact rescan; with 0.01 everywhere
+// ~3 % of random-logit anchors, i.e. 60 % of the warps, took it.)
 __device__ __forceinline__ float tie_window_threshold(float m) {
-  return (m > -80.0f && m < 15.0f) ? __fsub_rn(m, m > 8.0f ? 2.0f : 0.01f) : -INFINITY;
+  return (m > -80.0f && m < 15.0f) ? __fsub_rn(m, m > 8.0f ? 2.0f : (m > 2.0f ? 0.01f : 1e-4f)) : -INFINITY;
 }
 
 }  // namespace tod
