@@ -330,7 +330,7 @@ def main():
                 "launches": len(conv_rows), "flop_per_launch_avg": conv_gflop * 1e9 / max(len(conv_rows), 1),
                 "avg_launch_ms": conv_ms / max(len(conv_rows), 1), "conv_share_of_eager_pass": conv_ms / all_ms if all_ms else None}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # N = 1 only: the other ranks' barrier spin would share the cores
             v, cores, runs = cpu_oracle_rate(args.scale, args.size, 8, 10.0, 6)
             cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": f"8 images per run x {runs} runs of the CPU oracle (fp32 torch forward + decode + numpy NMS), median"}
