@@ -408,15 +408,15 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   // Auto follows the per-layer measurements in profiles/r1_conv_bench_*.txt: the halo kernel (1 CTA/SM, patch reuse,
   // resident weights, specialised TMA-store epilogue) wins on maps >= 40 wide and on almost every 1x1 conv; the per-tap
   // kernel (2 CTAs/SM) still wins where 16x8 patches tile the map badly (20x20), on stride 2 with > 32 input channels
-  // (four parity patches per chunk), on wide-K / narrow-N 3x3 layers (cin >= 128 into <= 64 channels, or cin > 128 on a
-  // 40-wide map) and on the tiny 1x1 head outputs.
+  // (four parity patches per chunk) and on the tiny 1x1 head outputs.
   int variant = d->reserved[0];
   if (variant == 0) {
     const int wout = d->win / d->stride;
     const long long mtot = static_cast<long long>(d->batch) * (d->hin / d->stride) * wout;
     bool halo;
     if (d->ksize == 3 && d->stride == 2) halo = d->cin <= 32;
-    else if (d->ksize == 3) halo = wout >= 40 && !(d->cin >= 128 && d->cout <= 64) && !(wout < 64 && d->cin > 128);
+    else if (d->ksize == 3) halo = wout >= 40;   // (wide-K / narrow-N layers went to the per-tap kernel until the halo
+                                                 // kernel's MMA role was unrolled: 256->128 @40^2 now 65.9 vs 71.9 us)
     else halo = !(mtot <= 32768 && d->cout <= 128);
     variant = halo ? 2 : 1;
   }
