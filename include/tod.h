@@ -103,6 +103,25 @@ typedef struct tod_head_fuse_desc {
 
 int tod_conv2d_head_decode(const tod_conv_desc* desc, const tod_head_fuse_desc* fuse, void* stream);
 
+/*
+ * A conv followed by a 1x1 conv on its output, the intermediate kept on chip ("back-to-back GEMM"): the first conv's
+ * activated bf16 tile is written to shared memory in the tcgen05 A-operand layout and a second MMA with the resident
+ * 1x1 weights produces the final tile; the intermediate tensor is never written to or read from HBM.
+ * Replaces: a Conv (model/blocks.py:52-54) whose only consumer is C2f.cv1 (model/blocks.py:104), e.g.
+ *           backbone.dark2[0] -> backbone.dark2[1].cv1 (model/backbone.py:23-25), bit-identical to the two separate calls.
+ * Supported: first conv with 64 output channels, bf16 out, SiLU, no residual / upadd; tail 64 -> 64, SiLU.
+ *   desc: the first conv (d_out ignored);  d_w2 bf16 [64, 64] (tod_conv_weight_layout for cin 64, ksize 1), d_bias2 f32 [64]
+ *   d_out2 bf16 [batch, hout, wout, out2_pitch]
+ */
+typedef struct tod_conv_tail_desc {
+  const void* d_w2;
+  const float* d_bias2;
+  void* d_out2;
+  int32_t cout2, out2_pitch, act2;
+  int32_t reserved[5];
+} tod_conv_tail_desc;
+int tod_conv2d_tail1x1(const tod_conv_desc* desc, const tod_conv_tail_desc* tail, void* stream);
+
 /* Packed-weight geometry for a conv: *block_k (TMA/UMMA K chunk), *cin_pad (cin rounded up to block_k),
  * *k_total = ksize*ksize*cin_pad.  Host packers lay weights out as [cout][tap][cin_pad] bf16, zero padded. */
 int tod_conv_weight_layout(int32_t cin, int32_t ksize, int32_t block_k_hint,

@@ -130,3 +130,54 @@ def test_conv_rejects_bad_arguments():
     assert _lib.lib().tod_conv2d_nhwc_bf16(C.byref(d), None) == -1      # cin % 16 != 0
     d.cin, d.ksize = 16, 5
     assert _lib.lib().tod_conv2d_nhwc_bf16(C.byref(d), None) == -1      # unsupported kernel size
+
+
+# ------------------------------------------------------------------------------------------ fused 1x1 tail (back-to-back GEMM)
+TAIL_CASES = [
+    ("3x3s2_c32_160", 2, 160, 160, 32, 3, 2),      # backbone.dark2.0 -> dark2.1.cv1 geometry (scale s)
+    ("3x3s2_c32_ragged", 1, 40, 56, 32, 3, 2),
+    ("3x3_c64", 2, 24, 40, 64, 3, 1),
+    ("1x1_c128", 1, 20, 20, 128, 1, 1),
+    ("3x3_c16_tiny", 3, 6, 6, 16, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case_def", TAIL_CASES, ids=[c[0] for c in TAIL_CASES])
+def test_conv_tail1x1_equals_two_separate_convs(case_def):
+    """tod_conv2d_tail1x1 (conv -> SiLU -> bf16 panel in shared memory -> 1x1 conv -> SiLU) against the same two convs
+    through tod_conv2d_nhwc_bf16 with the intermediate in HBM: same rounding points, so the outputs must be bit-identical;
+    channel-window output (pitch 96, offset 32) like the C2f concat buffer."""
+    import ctypes as C
+    from tests import gpu_util as U
+    from transparent_object_detection_b200 import _lib
+    from transparent_object_detection_b200._lib import ConvDesc, ConvTailDesc, check
+    from transparent_object_detection_b200.engine import pack_conv_weight
+    _, B, H, W, cin, k, stride = case_def
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn((B, H, W, cin), generator=g).to(torch.bfloat16).cuda()
+    w1 = torch.randn((64, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b1 = torch.randn((64,), generator=g) * 0.5
+    w2 = torch.randn((64, 64, 1, 1), generator=g) * (2.0 / 64) ** 0.5
+    b2 = torch.randn((64,), generator=g) * 0.5
+    Ho, Wo = H // stride, W // stride
+    mid = torch.zeros((B, Ho, Wo, 64), dtype=torch.bfloat16, device="cuda")
+    want = torch.full((B, Ho, Wo, 96), 7.0, dtype=torch.bfloat16, device="cuda")
+    U.run_conv(x, 0, cin, w1, b1, mid, 0, stride, 1, variant=2)
+    U.run_conv(mid, 0, 64, w2, b2, want, 32, 1, 1, variant=2)
+    got = torch.full_like(want, 7.0)
+    wp1, wp2 = pack_conv_weight(w1, 0).cuda(), pack_conv_weight(w2, 0).cuda()
+    bb1, bb2 = b1.cuda().contiguous(), b2.cuda().contiguous()
+    d = ConvDesc()
+    d.d_x, d.d_w, d.d_bias = x.data_ptr(), wp1.data_ptr(), bb1.data_ptr()
+    d.batch, d.hin, d.win, d.cin, d.cout, d.ksize, d.stride = B, H, W, cin, 64, k, stride
+    d.x_pitch, d.out_pitch, d.act, d.out_dtype = cin, 64, 1, 0
+    t = ConvTailDesc()
+    t.d_w2, t.d_bias2, t.d_out2 = wp2.data_ptr(), bb2.data_ptr(), got.data_ptr() + 32 * 2
+    t.cout2, t.out2_pitch, t.act2 = 64, 96, 1
+    check(_lib.lib().tod_conv2d_tail1x1(C.byref(d), C.byref(t), U.stream()), "tail")
+    torch.cuda.synchronize()
+    assert torch.equal(got[..., :32], torch.full_like(got[..., :32], 7.0)) and torch.equal(got[..., 96 - 0:], got[..., 96:])
+    assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+    ref = U.conv_reference(U.conv_reference(x, 0, cin, w1, b1, stride, 1).to(torch.bfloat16), 0, 64, w2, b2, 1, 1)
+    err = (got[..., 32:].float() - ref).abs()
+    assert float((err > 2e-2 + 2e-2 * ref.abs()).float().mean()) == 0.0

@@ -16,7 +16,7 @@ SYMBOLS = (
     "tod_stem_conv_nchw_f32", "tod_sppf_pool_nhwc_bf16", "tod_head_decode", "tod_nms_prepare_dense",
     "tod_nms_workspace_bytes", "tod_nms", "tod_conv2d_nhwc_bf16_simt_check", "tod_decode_box_from_head",
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
-    "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes",
+    "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
 )
 
 
@@ -63,6 +63,11 @@ class LetterboxDesc(C.Structure):
     ]
 
 
+class ConvTailDesc(C.Structure):
+    _fields_ = [("d_w2", C.c_void_p), ("d_bias2", C.c_void_p), ("d_out2", C.c_void_p),
+                ("cout2", C.c_int32), ("out2_pitch", C.c_int32), ("act2", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
 TOD_FUSE_BOX, TOD_FUSE_CLS = 1, 2
 
 
@@ -107,6 +112,7 @@ def lib() -> C.CDLL:
     L.tod_debug_set_conv_profile.argtypes = [C.c_void_p]
     L.tod_resample_coeffs_bicubic.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]
+    L.tod_conv2d_tail1x1.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvTailDesc), C.c_void_p]
     L.tod_correct_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)  # fail loudly if the binary is stale

@@ -29,6 +29,7 @@
 namespace tod {
 
 constexpr int kHaloThreads = 320;
+constexpr int kHaloThreadsTail = 352;   // + one warp that issues the second GEMM of the fused 1x1 tail (EXTRA 7)
 constexpr int kMaxA = 4;      // A-ring slots
 constexpr int kMaxB = 40;     // B-ring slots (>= taps * chunks when the weights are resident)
 constexpr int kPatchH = 16, kPatchW = 8;
@@ -104,6 +105,10 @@ struct __align__(64) HaloParams {
   float* cand_box;
   float* cand_conf;
   int* cand_cls;
+  // fused 1x1 tail (EXTRA 7): y2 = act(W2 . act(conv) + b2); W2 [64 x 64] bf16 resident in shared memory
+  CUtensorMap tm_w2;
+  const float* bias2;
+  uint32_t off_w2, idesc2, hi_w2, hi_stage;
   unsigned long long* prof;  // optional per-CTA wait counters (tools/conv_profile.py), null in production
 };
 
@@ -275,13 +280,20 @@ __device__ __forceinline__ void wait_set(const uint32_t (&bars)[4], const uint32
 }
 
 template <bool SILU, bool OUT_F32, int EXTRA>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(EXTRA == 7 ? kHaloThreadsTail : kHaloThreads, 1)
+conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
   __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t res_full_bar[4];   // residual ring: 2 slots per epilogue group
   __shared__ __align__(16) float bias_s[256];
+  // EXTRA 7 only (static + dynamic shared memory of the other variants already sits 252 bytes under the 227 KB limit)
+  __shared__ __align__(16) float bias2_s[EXTRA == 7 ? 64 : 4];
+  __shared__ __align__(8) uint64_t tail_bars[EXTRA == 7 ? 5 : 1];   // tail weights landed / panel ready x2 / tail done x2
+  uint64_t& w2_full_bar = tail_bars[0];
+  uint64_t* const p_full_bar = &tail_bars[EXTRA == 7 ? 1 : 0];
+  uint64_t* const d2_full_bar = &tail_bars[EXTRA == 7 ? 3 : 0];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -315,6 +327,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
       mbar_init(&tmem_empty_bar[a], 4);
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_full_bar[a], 1);
+    if (EXTRA == 7) {
+      mbar_init(&w2_full_bar, 1);
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&p_full_bar[a], 1);
+        mbar_init(&d2_full_bar[a], 1);
+      }
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -324,6 +343,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.block_n; i += kHaloThreads - 64)
       bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) * (SILU ? 0.5f : 1.0f) : 0.0f;
+    if (EXTRA == 7 && threadIdx.x - 64 < 64)
+      bias2_s[threadIdx.x - 64] = p.bias2 != nullptr ? __ldg(p.bias2 + threadIdx.x - 64) * (SILU ? 0.5f : 1.0f) : 0.0f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -345,6 +366,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
             mbar_arrive_expect_tx(&b_full[i], p.b_tx_bytes);
             tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, (t * p.chunks + c) * p.block_k, n0);
           }
+      }
+      if (EXTRA == 7) {
+        mbar_arrive_expect_tx(&w2_full_bar, 64u * 128u);
+        tma_load_2d(&p.tm_w2, &w2_full_bar, smem_base + p.off_w2, 0, 0);
       }
       // Everything above (and the weights just requested) is independent of earlier kernels.  Activations, residual
       // and upsample-add operands and the output buffer are not: every access to them in this grid is ordered after
@@ -540,9 +565,42 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     }
     }   // elected lane
     __syncwarp();
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ EXTRA 7: issuer of the fused 1x1 tail.  An
+    // epilogue group turns a sub-tile's accumulator into the activated bf16 panel in its staging buffer -- 128 rows x
+    // 128 B, SWIZZLE_128B: exactly the canonical K-major A operand for K = 64 -- and signals p_full; this thread issues
+    // D2[group] = panel . W2^T (four K steps) and commits d2_full; the group reads D2 back, applies bias2 / activation
+    // and stores through the same staging buffer.  The intermediate never reaches memory.
+    if (EXTRA == 7 && elect_one()) {
+      int total[2] = {0, 0};
+      const int n_it = sched.iters();
+      for (int it = 0; it < n_it; ++it) {
+        int s0, m_cur;
+        sched.get(it, s0, m_cur);
+        total[it & 1] += m_cur;
+      }
+      wait_addr(smem_u32(&w2_full_bar), 0);
+      const uint32_t w2_lo = umma_desc_lo(smem_base + p.off_w2);
+      int done[2] = {0, 0};
+      const long long t_start = clock64();
+      while (done[0] < total[0] || done[1] < total[1]) {
+        if (clock64() - t_start > 8000000000ll) halo_wait_timeout(smem_u32(&p_full_bar[0]), 77u);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (done[g] < total[g] && try_wait_addr(smem_u32(&p_full_bar[g]), done[g] & 1)) {
+            tcgen05_fence_after();
+            const uint32_t a_lo = umma_desc_lo(smem_base + p.off_stage + g * kStageBytes);
+            umma_bf16_k4(tmem_base + 2 * acc_cols + g * 64, a_lo, p.hi_stage, w2_lo, p.hi_w2, p.idesc2, 0u);
+            umma_commit(&d2_full_bar[g]);
+            ++done[g];
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
-    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5 || EXTRA == 6)), "extra operands are only combined with bf16 output");
+    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5 || EXTRA == 6 || EXTRA == 7)), "extra operands are only combined with bf16 output");
     // EXTRA 5 = the bf16 residual of EXTRA 1, but its panels arrive through a two-slot TMA ring in shared memory (requested
     // by the group's leader two panels ahead) instead of per-thread register loads: with 8 epilogue warps the register
     // path keeps only ~16 KB in flight per SM and the residual read ran at ~2 TB/s next to everything else.
@@ -551,7 +609,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     // pixel (y, x) reads low-resolution row (y/2)*4 + x/2.  The register path issued 8 LDG.128 per 32 columns per thread
     // whose lanes hit 16 different 512-byte-apart rows; the epilogue, not HBM, bounded those layers (MMA role waited for
     // a free accumulator 77 % of the kernel).
-    constexpr int MX = EXTRA == 5 ? 1 : (EXTRA == 6 ? 2 : EXTRA);   // arithmetic flavour of the extra operand
+    constexpr int MX = EXTRA == 5 ? 1 : (EXTRA == 6 ? 2 : (EXTRA == 7 ? 0 : EXTRA));   // arithmetic flavour of the extra operand
     constexpr bool RING = EXTRA == 5 || EXTRA == 6;
     static_assert((EXTRA != 3 && EXTRA != 4) || (OUT_F32 && !SILU), "the fused head decode consumes the f32 logits of a bare 1x1 conv");
     constexpr int kPanelCols = OUT_F32 ? 32 : 64;      // a full staging panel row is 128 bytes
@@ -717,8 +775,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
     };
     // The extra operand was written by an earlier kernel and its first chunk is requested BEFORE the accumulator wait
     // (the loads do not depend on this grid's MMAs), so these threads order themselves after the earlier grids directly.
-    if (EXTRA != 0) pdl_wait();
+    if (EXTRA != 0 && EXTRA != 7) pdl_wait();
     const int first_cols = min(32, p.block_n);
+    int tj = 0;   // EXTRA 7: sub-tiles this group has sent through the tail
     uint32_t lt = 0;
     const int n_it = sched.iters();
     // ---- residual ring (EXTRA 5): leader-side prefetch cursor over this group's panels, consumer-side panel counter
@@ -868,6 +927,32 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tcgen05(const __gri
           tw = wc.begin();
           named_bar_sync(bar_id, 128);
           wc.end(3, tw);
+          if constexpr (EXTRA == 7) {
+            // the activated panel is the A operand of the tail GEMM: hand it to the tail issuer, read D2 back
+            if (leader) mbar_arrive(&p_full_bar[group]);
+            wait_addr(smem_u32(&d2_full_bar[group]), tj & 1);
+            ++tj;
+            tcgen05_fence_after();
+            const uint32_t taddr2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * acc_cols + group * 64;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr2 + ch * 32, v);
+              tmem_ld_wait();
+              epilogue_math<32, SILU, OUT_F32, 0>(v, bias2_s + ch * 32, ex[0], false, &o[ch * kWordsPerChunk]);
+            }
+            tcgen05_fence_before();
+            // d2_full also means the tail MMAs have finished reading the staging panel: overwrite it with the output
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t off = swz(row_off + j * 16, p.smask);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + off), "r"(o[4 * j]), "r"(o[4 * j + 1]),
+                           "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+          }
           if (leader) {
             tma_store_4d(&p.tm_out, stage, n0 + col0, c1, c2, c3);
             bulk_commit_group();
@@ -904,7 +989,7 @@ static uint32_t desc_hi(uint32_t sbo_bytes, int bk) {
 // res_ring: 0 none, 1 bf16 residual panels, 2 f32 upsample-add panels (1x1 conv on 16x8 pixel tiles) through the
 // shared-memory TMA ring of the epilogue groups.
 static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits,
-                        int res_ring = 0) {
+                        int res_ring = 0, bool tail = false) {
   int rc;
   *fits = true;
   memset(&p, 0, sizeof(p));
@@ -1115,11 +1200,11 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 
   // ---- shared-memory plan: m sub-tiles per weight tile, A ring, B ring or resident weights
   // (+ four residual panels when the residual goes through the shared-memory ring; that plan needs resident weights)
-  const uint32_t staging = (res_ring ? 6 : 2) * kStageBytes;
-  const uint32_t budget = kHaloSmemLimit - 1024 - staging;
+  const uint32_t staging = (res_ring ? 6 : 2) * kStageBytes + (tail ? 8192u : 0u);   // tail: + the resident [64 x 64] W2
+  const uint32_t budget = kHaloSmemLimit - 1024 - staging - (tail ? 1024u : 0u);   // tail: its extra static shared memory
   const uint32_t b_total = static_cast<uint32_t>(taps) * p.chunks * p.b_slot_bytes;
   const bool may_station = taps * p.chunks <= kMaxB && d->reserved[2] != 1;
-  int m_max = 512 / (2 * p.block_n);
+  int m_max = (512 - (tail ? 128 : 0)) / (2 * p.block_n);   // tail: 2 x 64 TMEM columns for the second accumulators
   if (m_max > 4) m_max = 4;
   if (m_max < 1) m_max = 1;
   if (m_max > p.num_subtiles) m_max = p.num_subtiles;
@@ -1180,13 +1265,14 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.off_b = p.sa * p.a_slot_bytes;
   p.off_stage = p.off_b + p.sb * p.b_slot_bytes;
   p.off_res = p.off_stage + 2 * kStageBytes;
+  p.off_w2 = p.off_stage + (res_ring ? 6 : 2) * kStageBytes;
   const size_t smem = static_cast<size_t>(p.off_stage) + staging + 1024;   // staging includes the residual ring
-  TOD_CHECK_ARG(smem <= kHaloSmemLimit, "conv: shared-memory plan overflows (%zu bytes)", smem);
+  TOD_CHECK_ARG(smem <= kHaloSmemLimit - (tail ? 1024u : 0u), "conv: shared-memory plan overflows (%zu bytes)", smem);
   p.num_super = ceil_div(p.num_subtiles, p.m);
 
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * p.m * p.block_n)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(2 * p.m * p.block_n + (tail ? 128 : 0))) cols <<= 1;
   p.tmem_cols = cols;
 
   p.bias = d->d_bias;
@@ -1201,9 +1287,9 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 
 // kernel variants: [0..2] bf16 out, no activation, extra 0/1/2; [3..5] bf16 out, SiLU, extra 0/1/2; [6] f32 out, no
 // activation; [7] f32 out, SiLU; [8] fused box decode; [9] fused class decode; [10] bf16 out, SiLU, residual through
-// the shared-memory TMA ring; [11] bf16 out, SiLU, upsample-add through the ring
+// the shared-memory TMA ring; [11] bf16 out, SiLU, upsample-add through the ring; [12] bf16 out, SiLU, fused 1x1 tail
 using HaloKernel = void (*)(HaloParams);
-constexpr int kHaloVariants = 12;
+constexpr int kHaloVariants = 13;
 static HaloKernel halo_kernel(int i) {
   switch (i) {
     case 0: return conv_halo_tcgen05<false, false, 0>;
@@ -1217,7 +1303,8 @@ static HaloKernel halo_kernel(int i) {
     case 8: return conv_halo_tcgen05<false, true, 3>;
     case 9: return conv_halo_tcgen05<false, true, 4>;
     case 10: return conv_halo_tcgen05<true, false, 5>;
-    default: return conv_halo_tcgen05<true, false, 6>;
+    case 11: return conv_halo_tcgen05<true, false, 6>;
+    default: return conv_halo_tcgen05<true, false, 7>;
   }
 }
 
@@ -1225,7 +1312,7 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int i = 0; i < kHaloVariants && attr_err == cudaSuccess; ++i)
+    for (int i = 0; i < kHaloVariants - 1 && attr_err == cudaSuccess; ++i)   // (the tail variant sets its own, smaller limit)
       attr_err = cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit);
   });
   int rc;
@@ -1293,6 +1380,52 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
                        "conv_halo_tcgen05 launch")) != TOD_OK)
     return rc;
   return TOD_OK;
+}
+
+// Conv (64 output channels, SiLU) + a 1x1 conv 64 -> 64 (SiLU) on its output, the intermediate kept on chip (EXTRA 7).
+int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, void* stream) {
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(halo_kernel(12), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit - 1024);
+  });
+  int rc;
+  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_halo_tcgen05 tail)")) != TOD_OK) return rc;
+  TOD_CHECK_ARG(t != nullptr && t->d_w2 != nullptr && t->d_out2 != nullptr, "conv tail: null pointer");
+  TOD_CHECK_ARG(d->cout == 64 && t->cout2 == 64, "conv tail: needs 64 -> 64 (got %d -> %d)", d->cout, t->cout2);
+  TOD_CHECK_ARG(d->act == TOD_ACT_SILU && t->act2 == TOD_ACT_SILU, "conv tail: both convs must end in SiLU");
+  TOD_CHECK_ARG(d->d_residual == nullptr && d->d_upadd == nullptr && d->out_dtype == TOD_OUT_BF16, "conv tail: plain bf16 conv first");
+  TOD_CHECK_ARG(t->out2_pitch >= 64 && t->out2_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(t->d_out2) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(t->d_w2) & 15) == 0,
+                "conv tail: output pitch / alignment");
+  tod_conv_desc c = *d;          // the tensor map of the store describes the TAIL's output
+  c.d_out = t->d_out2;
+  c.out_pitch = t->out2_pitch;
+  HaloParams p;
+  size_t smem = 0;
+  bool fits = false;
+  const int bk0 = pick_block_k(c.cin, c.block_k);
+  const int cin_pad = round_up(c.cin, bk0);
+  for (int bk = bk0; bk >= 16 && !fits; bk >>= 1)
+    if ((rc = build_params(&c, bk, cin_pad, p, &smem, &fits, 0, true)) != TOD_OK) return rc;
+  TOD_CHECK_ARG(fits, "conv tail: no shared-memory plan fits");
+  TOD_CHECK_ARG(p.n_tiles == 1 && p.block_n == 64 && p.pc == 64, "conv tail: unexpected tiling");
+  {
+    const uint64_t dims[2] = {64, 64};
+    const uint64_t str[1] = {128};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = encode_map(&p.tm_w2, t->d_w2, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != TOD_OK) return rc;
+  }
+  p.bias2 = t->d_bias2;
+  p.hi_w2 = desc_hi(8 * 128, 64);
+  p.hi_stage = desc_hi(8 * 128, 64);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(64 >> 3) << 17) | ((128u >> 4) << 24);
+  const long long work = p.num_super;
+  long long grid = num_sms();
+  if (grid > work) grid = work;
+  return check_cuda(launch_pdl(halo_kernel(12), dim3(static_cast<unsigned>(grid)), dim3(kHaloThreadsTail), smem,
+                               static_cast<cudaStream_t>(stream), p),
+                    "conv_halo_tcgen05 (tail) launch");
 }
 
 }  // namespace tod

@@ -401,6 +401,16 @@ extern "C" int tod_conv2d_head_decode(const tod_conv_desc* d, const tod_head_fus
   return conv_halo_launch(&c, stream, fuse);
 }
 
+extern "C" int tod_conv2d_tail1x1(const tod_conv_desc* d, const tod_conv_tail_desc* tail, void* stream) {
+  TOD_CHECK_ARG(tail != nullptr, "conv tail: null descriptor");
+  tod_conv_desc c = *d;
+  if (c.d_out == nullptr) c.d_out = tail->d_out2;     // the intermediate is never stored
+  if (c.out_pitch < c.cout) c.out_pitch = c.cout;
+  int rc = validate(&c, false);
+  if (rc != TOD_OK) return rc;
+  return conv_halo_launch_tail(&c, tail, stream);
+}
+
 extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   int rc = validate(d);
   if (rc != TOD_OK) return rc;

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16,
+from ._lib import (ConvDesc, ConvTailDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16,
                    TOD_OUT_F32, check)
 
 BN_EPS = 1e-5
@@ -282,6 +282,21 @@ class DetectorEngine:
                 self.head_fuse[f"head.{tower}.{i}.4"] = f
             off += h * w
         self.fuse_head_decode = True    # graph_for: candidates straight from the head convs
+        # fused 1x1 tails (tod_conv2d_tail1x1): a conv with 64 output channels whose ONLY consumer is a 1x1 64 -> 64 conv
+        # (backbone.dark2[0] -> dark2[1].cv1 at scale s: 210 MB written and read back per batch-64 pass otherwise)
+        self.tail_fuse: Dict[str, Tuple[ConvTailDesc, str]] = {}
+        self.tail_skip = set()
+        if os.environ.get("TOD_FUSE_TAIL", "1") != "0":
+            a, b_ = self.conv_meta.get("backbone.dark2.0"), self.conv_meta.get("backbone.dark2.1.cv1")
+            if (a is not None and b_ is not None and a["dst"].c == 64 and a["dst"].pitch == 64 and b_["src"].ptr == a["dst"].ptr
+                    and b_["src"].c == 64 and b_["dst"].c == 64 and b_["w"].shape[-1] == 1 and b_["upadd"] is None
+                    and b_["residual"] is None and not b_["out_f32"] and b_["act"] == TOD_ACT_SILU and a["act"] == TOD_ACT_SILU):
+                db = next(p for k, n, p in self.ops if n == "backbone.dark2.1.cv1")
+                t = ConvTailDesc()
+                t.d_w2, t.d_bias2, t.d_out2 = db.d_w, db.d_bias, db.d_out
+                t.cout2, t.out2_pitch, t.act2 = 64, db.out_pitch, TOD_ACT_SILU
+                self.tail_fuse["backbone.dark2.0"] = (t, "backbone.dark2.1.cv1")
+                self.tail_skip.add("backbone.dark2.1.cv1")
 
     # ------------------------------------------------------------------ execution
     def _stream(self) -> int:
@@ -323,7 +338,11 @@ class DetectorEngine:
         def issue(kind, name, payload, stream):
             st = stream.cuda_stream
             if kind == "conv":
-                if fused_decode and name in self.head_fuse:
+                if name in self.tail_skip:
+                    return
+                if name in self.tail_fuse:
+                    check(L.tod_conv2d_tail1x1(C.byref(payload), C.byref(self.tail_fuse[name][0]), st), name)
+                elif fused_decode and name in self.head_fuse:
                     check(L.tod_conv2d_head_decode(C.byref(payload), C.byref(self.head_fuse[name]), st), name)
                 else:
                     check(L.tod_conv2d_nhwc_bf16(C.byref(payload), st), name)
@@ -394,7 +413,7 @@ class DetectorEngine:
     # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
     @property
     def launches_per_pass(self) -> int:
-        return len(self.ops) + (0 if self.fuse_head_decode else 1) + 3
+        return len(self.ops) - len(self.tail_skip) + (0 if self.fuse_head_decode else 1) + 3
 
     def capture(self, conf_thres: float, nms_thres: float, head_out: bool = False, decoded: bool = False) -> None:
         """Capture network + decode + NMS on the static input into one CUDA graph."""
