@@ -271,12 +271,15 @@ def main():
         for rep in range(reps):
             evs = []
             for kind, name, payload in eng.ops:
-                if kind == "conv" and name in eng.tail_skip:                # fused into the previous conv's epilogue
-                    continue
+                if kind == "conv" and (name in eng.tail_skip or (eng.fuse_head_decode and name in eng.tail_box_skip)):
+                    continue                                                # fused into the previous conv's epilogue
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 if kind == "conv":
-                    if name in eng.tail_fuse:
+                    if eng.fuse_head_decode and name in eng.tail_box:
+                        tb, fb = eng.tail_box[name]
+                        check(eng.L.tod_conv2d_tail1x1_box_decode(C.byref(payload), C.byref(tb), C.byref(fb), st), name)
+                    elif name in eng.tail_fuse:
                         check(eng.L.tod_conv2d_tail1x1(C.byref(payload), C.byref(eng.tail_fuse[name][0]), st), name)
                     elif eng.fuse_head_decode and name in eng.head_fuse:      # what the captured graph runs
                         check(eng.L.tod_conv2d_head_decode(C.byref(payload), C.byref(eng.head_fuse[name]), st), name)
@@ -308,7 +311,7 @@ def main():
                 ho, wo = dd.hin // dd.stride, dd.win // dd.stride
                 row["gflop"] = 2.0 * B * ho * wo * dd.cout * dd.cin * dd.ksize ** 2 / 1e9
                 row["shape"] = f"{dd.cin}->{dd.cout} k{dd.ksize} s{dd.stride} @{ho}x{wo}"
-                if name in eng.tail_fuse:                      # + the fused 1x1 conv's algorithmic FLOPs
+                if name in eng.tail_fuse or (eng.fuse_head_decode and name in eng.tail_box):   # + the fused 1x1 conv's FLOPs
                     row["gflop"] += 2.0 * B * ho * wo * 64 * 64 / 1e9
                     row["shape"] += " + 64->64 k1 (fused tail)"
                 row["tflops"] = row["gflop"] / row["ms"]

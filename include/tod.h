@@ -121,6 +121,11 @@ typedef struct tod_conv_tail_desc {
   int32_t reserved[5];
 } tod_conv_tail_desc;
 int tod_conv2d_tail1x1(const tod_conv_desc* desc, const tod_conv_tail_desc* tail, void* stream);
+/* The same with the tail being the bare 64 -> 64 box-logit conv of a head tower (model/head.py:36-42, act2 = NONE) and its
+ * DFL / dist2bbox decode (tod_conv2d_head_decode, mode TOD_FUSE_BOX): Conv3x3 + Conv1x1 + decode in one kernel, neither
+ * the tower's last activation nor the logits reach memory; candidates bit-identical to the separate calls. */
+int tod_conv2d_tail1x1_box_decode(const tod_conv_desc* desc, const tod_conv_tail_desc* tail,
+                                  const tod_head_fuse_desc* fuse, void* stream);
 
 /* Packed-weight geometry for a conv: *block_k (TMA/UMMA K chunk), *cin_pad (cin rounded up to block_k),
  * *k_total = ksize*ksize*cin_pad.  Host packers lay weights out as [cout][tap][cin_pad] bf16, zero padded. */

@@ -352,13 +352,15 @@ def test_detector_graph_matches_eager_and_oracle_nms():
     assert any(w is not None for w in want)
 
 
-def test_fused_head_decode_equals_conv_then_decode_bit_for_bit():
-    """tod_conv2d_head_decode (last conv of a head tower + its share of the decode in the conv epilogue) must give
-    exactly the candidates of the unfused path (f32 raw maps -> tod_head_decode), at a batch / size whose flat 128-row
-    tiles straddle images and end in a partial tile."""
+@pytest.mark.parametrize("scale", ["n", "s"])
+def test_fused_head_decode_equals_conv_then_decode_bit_for_bit(scale):
+    """tod_conv2d_head_decode (last conv of a head tower + its share of the decode in the conv epilogue) and
+    tod_conv2d_tail1x1_box_decode (the box tower's last TWO convs + decode in one kernel) must give exactly the
+    candidates of the unfused path (f32 raw maps -> tod_head_decode), at a batch / size whose flat 128-row tiles straddle
+    images and end in a partial tile."""
     from oracle import synth
     from transparent_object_detection_b200 import BaseModel
-    C_, d, m = synth.SCALES["n"]
+    C_, d, m = synth.SCALES[scale]
     model = BaseModel(80, C_, d, m).eval()
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
     eng = model.engine(3, 96, 160)
@@ -371,6 +373,7 @@ def test_fused_head_decode_equals_conv_then_decode_bit_for_bit():
         t.fill_(-7)
     eng.run_network(x, fused_decode=True)
     torch.cuda.synchronize()
+    assert len(eng.tail_box) == 3                       # the box towers went through the fused tail
     assert torch.equal(eng.cand_cls, want[2])
     assert torch.equal(eng.cand_conf, want[1])
     assert torch.equal(eng.cand_box, want[0])

@@ -17,6 +17,7 @@ SYMBOLS = (
     "tod_nms_workspace_bytes", "tod_nms", "tod_conv2d_nhwc_bf16_simt_check", "tod_decode_box_from_head",
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
     "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
+    "tod_conv2d_tail1x1_box_decode",
 )
 
 
@@ -113,6 +114,7 @@ def lib() -> C.CDLL:
     L.tod_resample_coeffs_bicubic.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]
     L.tod_conv2d_tail1x1.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvTailDesc), C.c_void_p]
+    L.tod_conv2d_tail1x1_box_decode.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvTailDesc), C.POINTER(HeadFuseDesc), C.c_void_p]
     L.tod_correct_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)  # fail loudly if the binary is stale

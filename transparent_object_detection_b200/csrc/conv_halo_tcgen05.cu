@@ -280,7 +280,7 @@ __device__ __forceinline__ void wait_set(const uint32_t (&bars)[4], const uint32
 }
 
 template <bool SILU, bool OUT_F32, int EXTRA>
-__global__ void __launch_bounds__(EXTRA == 7 ? kHaloThreadsTail : kHaloThreads, 1)
+__global__ void __launch_bounds__((EXTRA == 7 || EXTRA == 8) ? kHaloThreadsTail : kHaloThreads, 1)
 conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
@@ -288,12 +288,15 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t res_full_bar[4];   // residual ring: 2 slots per epilogue group
   __shared__ __align__(16) float bias_s[256];
-  // EXTRA 7 only (static + dynamic shared memory of the other variants already sits 252 bytes under the 227 KB limit)
-  __shared__ __align__(16) float bias2_s[EXTRA == 7 ? 64 : 4];
-  __shared__ __align__(8) uint64_t tail_bars[EXTRA == 7 ? 5 : 1];   // tail weights landed / panel ready x2 / tail done x2
+  // Fused 1x1 tail: EXTRA 7 stores act(W2 . y + b2); EXTRA 8 (last two convs of a box tower, model/head.py:36-42) decodes
+  // W2 . y + b2 straight into the NMS box candidates like EXTRA 3.  (Tail-only shared memory: static + dynamic of the
+  // other variants already sits 252 bytes under the 227 KB limit.)
+  constexpr bool TAIL = EXTRA == 7 || EXTRA == 8;
+  __shared__ __align__(16) float bias2_s[TAIL ? 64 : 4];
+  __shared__ __align__(8) uint64_t tail_bars[TAIL ? 5 : 1];   // tail weights landed / panel ready x2 / tail done x2
   uint64_t& w2_full_bar = tail_bars[0];
-  uint64_t* const p_full_bar = &tail_bars[EXTRA == 7 ? 1 : 0];
-  uint64_t* const d2_full_bar = &tail_bars[EXTRA == 7 ? 3 : 0];
+  uint64_t* const p_full_bar = &tail_bars[TAIL ? 1 : 0];
+  uint64_t* const d2_full_bar = &tail_bars[TAIL ? 3 : 0];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -327,7 +330,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       mbar_init(&tmem_empty_bar[a], 4);
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_full_bar[a], 1);
-    if (EXTRA == 7) {
+    if (TAIL) {
       mbar_init(&w2_full_bar, 1);
       for (int a = 0; a < 2; ++a) {
         mbar_init(&p_full_bar[a], 1);
@@ -343,8 +346,8 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.block_n; i += kHaloThreads - 64)
       bias_s[i] = (p.bias != nullptr && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) * (SILU ? 0.5f : 1.0f) : 0.0f;
-    if (EXTRA == 7 && threadIdx.x - 64 < 64)
-      bias2_s[threadIdx.x - 64] = p.bias2 != nullptr ? __ldg(p.bias2 + threadIdx.x - 64) * (SILU ? 0.5f : 1.0f) : 0.0f;
+    if (TAIL && threadIdx.x - 64 < 64)   // (pre-halved for the SiLU of EXTRA 7; the box logits of EXTRA 8 take it as it is)
+      bias2_s[threadIdx.x - 64] = p.bias2 != nullptr ? __ldg(p.bias2 + threadIdx.x - 64) * (EXTRA == 7 && SILU ? 0.5f : 1.0f) : 0.0f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -367,7 +370,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
             tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, (t * p.chunks + c) * p.block_k, n0);
           }
       }
-      if (EXTRA == 7) {
+      if (TAIL) {
         mbar_arrive_expect_tx(&w2_full_bar, 64u * 128u);
         tma_load_2d(&p.tm_w2, &w2_full_bar, smem_base + p.off_w2, 0, 0);
       }
@@ -571,7 +574,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     // 128 B, SWIZZLE_128B: exactly the canonical K-major A operand for K = 64 -- and signals p_full; this thread issues
     // D2[group] = panel . W2^T (four K steps) and commits d2_full; the group reads D2 back, applies bias2 / activation
     // and stores through the same staging buffer.  The intermediate never reaches memory.
-    if (EXTRA == 7 && elect_one()) {
+    if (TAIL && elect_one()) {
       int total[2] = {0, 0};
       const int n_it = sched.iters();
       for (int it = 0; it < n_it; ++it) {
@@ -600,7 +603,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
-    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5 || EXTRA == 6 || EXTRA == 7)), "extra operands are only combined with bf16 output");
+    static_assert(!(OUT_F32 && (EXTRA == 1 || EXTRA == 2 || EXTRA == 5 || EXTRA == 6 || EXTRA == 7 || EXTRA == 8)), "extra operands are only combined with bf16 output");
     // EXTRA 5 = the bf16 residual of EXTRA 1, but its panels arrive through a two-slot TMA ring in shared memory (requested
     // by the group's leader two panels ahead) instead of per-thread register loads: with 8 epilogue warps the register
     // path keeps only ~16 KB in flight per SM and the residual read ran at ~2 TB/s next to everything else.
@@ -609,7 +612,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     // pixel (y, x) reads low-resolution row (y/2)*4 + x/2.  The register path issued 8 LDG.128 per 32 columns per thread
     // whose lanes hit 16 different 512-byte-apart rows; the epilogue, not HBM, bounded those layers (MMA role waited for
     // a free accumulator 77 % of the kernel).
-    constexpr int MX = EXTRA == 5 ? 1 : (EXTRA == 6 ? 2 : (EXTRA == 7 ? 0 : EXTRA));   // arithmetic flavour of the extra operand
+    constexpr int MX = EXTRA == 5 ? 1 : (EXTRA == 6 ? 2 : ((EXTRA == 7 || EXTRA == 8) ? 0 : EXTRA));   // arithmetic flavour of the extra operand
     constexpr bool RING = EXTRA == 5 || EXTRA == 6;
     static_assert((EXTRA != 3 && EXTRA != 4) || (OUT_F32 && !SILU), "the fused head decode consumes the f32 logits of a bare 1x1 conv");
     constexpr int kPanelCols = OUT_F32 ? 32 : 64;      // a full staging panel row is 128 bytes
@@ -775,7 +778,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     };
     // The extra operand was written by an earlier kernel and its first chunk is requested BEFORE the accumulator wait
     // (the loads do not depend on this grid's MMAs), so these threads order themselves after the earlier grids directly.
-    if (EXTRA != 0 && EXTRA != 7) pdl_wait();
+    if (EXTRA != 0 && EXTRA != 7 && EXTRA != 8) pdl_wait();
     const int first_cols = min(32, p.block_n);
     int tj = 0;   // EXTRA 7: sub-tiles this group has sent through the tail
     uint32_t lt = 0;
@@ -927,6 +930,35 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
           tw = wc.begin();
           named_bar_sync(bar_id, 128);
           wc.end(3, tw);
+          if constexpr (EXTRA == 8) {
+            // box tower: D2 = the 4 x 16 DFL logits of this row's anchor -> distances -> NMS corners (EXTRA 3's arithmetic)
+            if (leader) mbar_arrive(&p_full_bar[group]);
+            wait_addr(smem_u32(&d2_full_bar[group]), tj & 1);
+            ++tj;
+            tcgen05_fence_after();
+            const uint32_t taddr2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * acc_cols + group * 64;
+            float dist[4];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr2 + ch * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int sd = 0; sd < 2; ++sd) {
+                float l[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) l[i] = __fadd_rn(__uint_as_float(v[sd * 16 + i]), bias2_s[ch * 32 + sd * 16 + i]);
+                dist[ch * 2 + sd] = dfl_side(l);
+              }
+            }
+            tcgen05_fence_before();
+            const int ah = c2 + (r >> 3), aw = c1 + (r & 7);
+            if (ah < p.hout && aw < p.wout) {
+              const size_t g = static_cast<size_t>(c3) * p.dec_anchors + p.dec_level_off + ah * p.wout + aw;
+              const float4 bpx = box_xywh_px(dist[0], dist[1], dist[2], dist[3], aw, ah, p.dec_stride);
+              reinterpret_cast<float4*>(p.cand_box)[g] = box_corners_norm(bpx, p.dec_in_w, p.dec_in_h);
+            }
+          }
           if constexpr (EXTRA == 7) {
             // the activated panel is the A operand of the tail GEMM: hand it to the tail issuer, read D2 back
             if (leader) mbar_arrive(&p_full_bar[group]);
@@ -953,7 +985,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
           }
-          if (leader) {
+          if (EXTRA != 8 && leader) {
             tma_store_4d(&p.tm_out, stage, n0 + col0, c1, c2, c3);
             bulk_commit_group();
           }
@@ -1289,7 +1321,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 // activation; [7] f32 out, SiLU; [8] fused box decode; [9] fused class decode; [10] bf16 out, SiLU, residual through
 // the shared-memory TMA ring; [11] bf16 out, SiLU, upsample-add through the ring; [12] bf16 out, SiLU, fused 1x1 tail
 using HaloKernel = void (*)(HaloParams);
-constexpr int kHaloVariants = 13;
+constexpr int kHaloVariants = 14;
 static HaloKernel halo_kernel(int i) {
   switch (i) {
     case 0: return conv_halo_tcgen05<false, false, 0>;
@@ -1304,7 +1336,8 @@ static HaloKernel halo_kernel(int i) {
     case 9: return conv_halo_tcgen05<false, true, 4>;
     case 10: return conv_halo_tcgen05<true, false, 5>;
     case 11: return conv_halo_tcgen05<true, false, 6>;
-    default: return conv_halo_tcgen05<true, false, 7>;
+    case 12: return conv_halo_tcgen05<true, false, 7>;
+    default: return conv_halo_tcgen05<true, false, 8>;
   }
 }
 
@@ -1312,7 +1345,7 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int i = 0; i < kHaloVariants - 1 && attr_err == cudaSuccess; ++i)   // (the tail variant sets its own, smaller limit)
+    for (int i = 0; i < kHaloVariants - 2 && attr_err == cudaSuccess; ++i)   // (the tail variants set their own, smaller limit)
       attr_err = cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit);
   });
   int rc;
@@ -1383,24 +1416,35 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
 }
 
 // Conv (64 output channels, SiLU) + a 1x1 conv 64 -> 64 (SiLU) on its output, the intermediate kept on chip (EXTRA 7).
-int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, void* stream) {
+int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, void* stream, const tod_head_fuse_desc* fuse) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(halo_kernel(12), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit - 1024);
+    for (int i = 12; i <= 13 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit - 1024);
   });
   int rc;
   if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_halo_tcgen05 tail)")) != TOD_OK) return rc;
-  TOD_CHECK_ARG(t != nullptr && t->d_w2 != nullptr && t->d_out2 != nullptr, "conv tail: null pointer");
+  TOD_CHECK_ARG(t != nullptr && t->d_w2 != nullptr && (t->d_out2 != nullptr || fuse != nullptr), "conv tail: null pointer");
   TOD_CHECK_ARG(d->cout == 64 && t->cout2 == 64, "conv tail: needs 64 -> 64 (got %d -> %d)", d->cout, t->cout2);
-  TOD_CHECK_ARG(d->act == TOD_ACT_SILU && t->act2 == TOD_ACT_SILU, "conv tail: both convs must end in SiLU");
+  TOD_CHECK_ARG(d->act == TOD_ACT_SILU && t->act2 == (fuse ? TOD_ACT_NONE : TOD_ACT_SILU),
+                "conv tail: SiLU conv, then a SiLU 1x1 conv (or the bare box-logit conv when decoding)");
   TOD_CHECK_ARG(d->d_residual == nullptr && d->d_upadd == nullptr && d->out_dtype == TOD_OUT_BF16, "conv tail: plain bf16 conv first");
-  TOD_CHECK_ARG(t->out2_pitch >= 64 && t->out2_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(t->d_out2) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(t->d_w2) & 15) == 0,
-                "conv tail: output pitch / alignment");
+  TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(t->d_w2) & 15) == 0, "conv tail: weight alignment");
   tod_conv_desc c = *d;          // the tensor map of the store describes the TAIL's output
-  c.d_out = t->d_out2;
-  c.out_pitch = t->out2_pitch;
+  if (fuse != nullptr) {         // nothing is stored: candidates only
+    TOD_CHECK_ARG(fuse->mode == TOD_FUSE_BOX && fuse->d_cand_box != nullptr && (reinterpret_cast<uintptr_t>(fuse->d_cand_box) & 15) == 0 &&
+                      d->ksize == 3 && d->stride == 1 && fuse->anchors > 0 && fuse->level_off >= 0 &&
+                      fuse->level_off + d->hin * d->win <= fuse->anchors && fuse->in_h > 0 && fuse->in_w > 0 && fuse->stride > 0.0f,
+                  "conv tail + box decode: bad descriptor");
+    c.d_out = const_cast<void*>(d->d_x);
+    c.out_pitch = d->x_pitch >= 64 ? d->x_pitch : 64;
+  } else {
+    TOD_CHECK_ARG(t->out2_pitch >= 64 && t->out2_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(t->d_out2) & 15) == 0,
+                  "conv tail: output pitch / alignment");
+    c.d_out = t->d_out2;
+    c.out_pitch = t->out2_pitch;
+  }
   HaloParams p;
   size_t smem = 0;
   bool fits = false;
@@ -1420,10 +1464,20 @@ int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, v
   p.hi_w2 = desc_hi(8 * 128, 64);
   p.hi_stage = desc_hi(8 * 128, 64);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(64 >> 3) << 17) | ((128u >> 4) << 24);
+  if (fuse != nullptr) {
+    TOD_CHECK_ARG(p.patch_mode, "conv tail + box decode: unexpected tiling");
+    p.dec_nc = fuse->nc;
+    p.dec_level_off = fuse->level_off;
+    p.dec_anchors = fuse->anchors;
+    p.dec_stride = fuse->stride;
+    p.dec_in_w = static_cast<float>(fuse->in_w);
+    p.dec_in_h = static_cast<float>(fuse->in_h);
+    p.cand_box = fuse->d_cand_box;
+  }
   const long long work = p.num_super;
   long long grid = num_sms();
   if (grid > work) grid = work;
-  return check_cuda(launch_pdl(halo_kernel(12), dim3(static_cast<unsigned>(grid)), dim3(kHaloThreadsTail), smem,
+  return check_cuda(launch_pdl(halo_kernel(fuse != nullptr ? 13 : 12), dim3(static_cast<unsigned>(grid)), dim3(kHaloThreadsTail), smem,
                                static_cast<cudaStream_t>(stream), p),
                     "conv_halo_tcgen05 (tail) launch");
 }

@@ -411,6 +411,17 @@ extern "C" int tod_conv2d_tail1x1(const tod_conv_desc* d, const tod_conv_tail_de
   return conv_halo_launch_tail(&c, tail, stream);
 }
 
+extern "C" int tod_conv2d_tail1x1_box_decode(const tod_conv_desc* d, const tod_conv_tail_desc* tail,
+                                             const tod_head_fuse_desc* fuse, void* stream) {
+  TOD_CHECK_ARG(tail != nullptr && fuse != nullptr, "conv tail + box decode: null descriptor");
+  tod_conv_desc c = *d;
+  if (c.d_out == nullptr) c.d_out = const_cast<void*>(c.d_x);   // neither the intermediate nor the logits are stored
+  if (c.out_pitch < c.cout) c.out_pitch = c.cout;
+  int rc = validate(&c, false);
+  if (rc != TOD_OK) return rc;
+  return conv_halo_launch_tail(&c, tail, stream, fuse);
+}
+
 extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   int rc = validate(d);
   if (rc != TOD_OK) return rc;

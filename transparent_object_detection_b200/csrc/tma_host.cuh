@@ -103,6 +103,7 @@ inline int pick_block_k(int cin, int hint) {
 
 // Entry of the halo-patch kernel (conv_halo_tcgen05.cu); the descriptor has already been validated.
 int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_desc* fuse = nullptr);
-int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, void* stream);
+int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, void* stream,
+                          const tod_head_fuse_desc* fuse = nullptr);
 
 }  // namespace tod

@@ -297,6 +297,21 @@ class DetectorEngine:
                 t.cout2, t.out2_pitch, t.act2 = 64, db.out_pitch, TOD_ACT_SILU
                 self.tail_fuse["backbone.dark2.0"] = (t, "backbone.dark2.1.cv1")
                 self.tail_skip.add("backbone.dark2.1.cv1")
+        # box towers on the fused-decode path (tod_conv2d_tail1x1_box_decode): Conv3x3 64 -> 64 + the bare 64 -> 64 logit
+        # conv + DFL / dist2bbox in one kernel per level (model/head.py:36-42,53-61)
+        self.tail_box: Dict[str, Tuple[ConvTailDesc, HeadFuseDesc]] = {}
+        self.tail_box_skip = set()
+        if os.environ.get("TOD_FUSE_TAIL", "1") != "0":
+            for i in range(len(self.level_shapes)):
+                na, nb = f"head.box.{i}.2", f"head.box.{i}.4"
+                a, b_ = self.conv_meta[na], self.conv_meta[nb]
+                if a["dst"].c == 64 and a["src"].c % 16 == 0 and b_["src"].ptr == a["dst"].ptr and b_["w"].shape[0] == 64:
+                    db = next(p for k, n, p in self.ops if n == nb)
+                    t = ConvTailDesc()
+                    t.d_w2, t.d_bias2, t.d_out2 = db.d_w, db.d_bias, None
+                    t.cout2, t.out2_pitch, t.act2 = 64, 64, TOD_ACT_NONE
+                    self.tail_box[na] = (t, self.head_fuse[nb])
+                    self.tail_box_skip.add(nb)
 
     # ------------------------------------------------------------------ execution
     def _stream(self) -> int:
@@ -338,9 +353,12 @@ class DetectorEngine:
         def issue(kind, name, payload, stream):
             st = stream.cuda_stream
             if kind == "conv":
-                if name in self.tail_skip:
+                if name in self.tail_skip or (fused_decode and name in self.tail_box_skip):
                     return
-                if name in self.tail_fuse:
+                if fused_decode and name in self.tail_box:
+                    t, f = self.tail_box[name]
+                    check(L.tod_conv2d_tail1x1_box_decode(C.byref(payload), C.byref(t), C.byref(f), st), name)
+                elif name in self.tail_fuse:
                     check(L.tod_conv2d_tail1x1(C.byref(payload), C.byref(self.tail_fuse[name][0]), st), name)
                 elif fused_decode and name in self.head_fuse:
                     check(L.tod_conv2d_head_decode(C.byref(payload), C.byref(self.head_fuse[name]), st), name)
@@ -413,7 +431,8 @@ class DetectorEngine:
     # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
     @property
     def launches_per_pass(self) -> int:
-        return len(self.ops) - len(self.tail_skip) + (0 if self.fuse_head_decode else 1) + 3
+        return (len(self.ops) - len(self.tail_skip) - (len(self.tail_box_skip) if self.fuse_head_decode else 0)
+                + (0 if self.fuse_head_decode else 1) + 3)
 
     def capture(self, conf_thres: float, nms_thres: float, head_out: bool = False, decoded: bool = False) -> None:
         """Capture network + decode + NMS on the static input into one CUDA graph."""
