@@ -252,6 +252,15 @@ __device__ __forceinline__ bool try_wait_addr(uint32_t bar, uint32_t parity) {
                : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time before it reports failure)
+__device__ __forceinline__ bool test_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void wait_addr(uint32_t bar, uint32_t parity) {
   if (try_wait_addr(bar, parity)) return;
   const long long t0 = clock64();
@@ -590,7 +599,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         if (clock64() - t_start > 8000000000ll) halo_wait_timeout(smem_u32(&p_full_bar[0]), 77u);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (done[g] < total[g] && try_wait_addr(smem_u32(&p_full_bar[g]), done[g] & 1)) {
+          if (done[g] < total[g] && test_wait_addr(smem_u32(&p_full_bar[g]), done[g] & 1)) {   // serve whichever group is ready
             tcgen05_fence_after();
             const uint32_t a_lo = umma_desc_lo(smem_base + p.off_stage + g * kStageBytes);
             umma_bf16_k4(tmem_base + 2 * acc_cols + g * 64, a_lo, p.hi_stage, w2_lo, p.hi_w2, p.idesc2, 0u);
