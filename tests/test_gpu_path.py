@@ -570,3 +570,30 @@ def test_every_scale_against_live_oracle(scale):
     if scale in ("n", "s"):
         assert float((out[:, :4] - want[:, :4]).abs().max()) <= 1.5
         assert float((out[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+
+
+@pytest.mark.parametrize("nc", [1, 3, 20])
+def test_network_with_few_classes_against_live_oracle(nc):
+    """Class counts other than 80 (the class conv is padded to 16 output channels, the class tower is max(C3, nc) wide):
+    head tensor within tolerance of the CPU oracle, Detector rows == the oracle's NMS on OUR decoded tensor, bit-exact."""
+    from oracle import detector_oracle as O, synth
+    from transparent_object_detection_b200 import BaseModel, DecodeBox, Detector
+    C_, d, m = synth.SCALES["n"]
+    sd = synth.make_state_dict(nc, C_, d, m, seed=0)
+    model = BaseModel(nc, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    x = torch.from_numpy(synth.make_images(2, 96, 128, seed=3))
+    out = model(x.cuda())
+    with torch.no_grad():
+        want = O.forward(sd, x, nc, d)
+    o = out.cpu()
+    assert tuple(o.shape) == (2, 4 + nc, 12 * 16 + 6 * 8 + 3 * 4)
+    assert float((o[:, :4] - want[:, :4]).abs().max()) <= 1.5
+    assert float((o[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+    db = DecodeBox(nc, (96, 128))
+    dec = db.decode_box(out)
+    conf = float(dec[:, :, 4:].max()) * 0.5                    # a threshold that keeps some anchors whatever the init
+    want_rows = O.non_max_suppression(dec.cpu().numpy().copy(), nc, (96, 128), (96, 128), True, conf, 0.5)
+    det = Detector(model, (96, 128), confidence=conf, nms_iou=0.5)
+    assert_dets_equal(det.detect(x), want_rows)
+    assert any(r is not None for r in want_rows)
