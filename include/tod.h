@@ -274,6 +274,26 @@ typedef struct tod_letterbox_desc {
 int tod_resample_coeffs_bicubic(int32_t in_size, int32_t out_size, int32_t* h_bounds, int32_t* h_coef, int32_t* ksize);
 int tod_letterbox_bicubic_u8(const tod_letterbox_desc* desc, void* stream);
 
+/*
+ * CBAM block on NHWC bf16 activations (block-level: not yet wired into the network plan).
+ * Replaces: CBAM.forward  model/blocks.py:206-223 (instances: model/backbone.py:26,40, model/head.py:28,30,39,41).
+ *   d_x bf16 [batch, h, w, x_pitch] -> d_out bf16 [batch, h, w, out_pitch] (may alias d_x), c channels (c % 8 == 0)
+ *   d_fc1 f32 [hidden, c], d_fc2 f32 [c, hidden] (the two bias-free 1x1 convs), d_conv f32 [2, ksize, ksize]
+ *   d_work f32, tod_cbam_workspace_floats(batch, h, w, c) elements (pooling partials, channel scale, per-pixel stats)
+ */
+typedef struct tod_cbam_desc {
+  const void* d_x;
+  void* d_out;
+  const float* d_fc1;
+  const float* d_fc2;
+  const float* d_conv;
+  float* d_work;
+  int32_t batch, h, w, c, hidden, ksize, x_pitch, out_pitch;
+  int32_t reserved[4];
+} tod_cbam_desc;
+int64_t tod_cbam_workspace_floats(int32_t batch, int32_t h, int32_t w, int32_t c);
+int tod_cbam_nhwc_bf16(const tod_cbam_desc* desc, void* stream);
+
 /* Debug/verification helper used by tests only: direct (non-tensor-core) evaluation of the same conv
  * descriptor on CUDA cores, fp32 accumulate.  Never called by the product path. */
 int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* desc, void* stream);

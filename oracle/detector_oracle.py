@@ -108,6 +108,31 @@ def sppf_pools(x: torch.Tensor) -> torch.Tensor:
     return torch.cat(y, 1)
 
 
+# ----------------------------------------------------------------------------- attention blocks
+def cbam(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """reference CBAM.forward, model/blocks.py:206-223: channel attention sigmoid(fc2(relu(fc1(avgpool))) +
+    fc2(relu(fc1(maxpool)))) (1x1 convs without bias, reduction 16), then spatial attention
+    sigmoid(conv7x7(cat[mean_c, max_c])) (padding 3, no bias) on the channel-scaled tensor."""
+    w1, w2, w7 = _t(sd, prefix + ".fc1.weight"), _t(sd, prefix + ".fc2.weight"), _t(sd, prefix + ".conv.weight")
+    mlp = lambda v: F.conv2d(F.relu(F.conv2d(v, w1)), w2)
+    ca = torch.sigmoid(mlp(F.adaptive_avg_pool2d(x, 1)) + mlp(F.adaptive_max_pool2d(x, 1)))
+    x = x * ca
+    st = torch.cat([x.mean(1, keepdim=True), x.max(1, keepdim=True)[0]], 1)
+    return x * torch.sigmoid(F.conv2d(st, w7, None, padding=w7.shape[-1] // 2))
+
+
+def self_attention(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """reference SelfAttention.forward, model/blocks.py:236-254: q, k = 1x1 convs to C/8 (+bias), v = 1x1 conv to C (+bias);
+    out[c, i] = sum_j v[c, j] * softmax_j(q_i . k_j); gamma * out + x."""
+    b, c, h, w = x.shape
+    q = F.conv2d(x, _t(sd, prefix + ".query.weight"), _t(sd, prefix + ".query.bias")).view(b, -1, h * w).permute(0, 2, 1)
+    k = F.conv2d(x, _t(sd, prefix + ".key.weight"), _t(sd, prefix + ".key.bias")).view(b, -1, h * w)
+    v = F.conv2d(x, _t(sd, prefix + ".value.weight"), _t(sd, prefix + ".value.bias")).view(b, -1, h * w)
+    att = torch.softmax(torch.bmm(q, k), dim=-1)
+    out = torch.bmm(v, att.permute(0, 2, 1)).view(b, c, h, w)
+    return _t(sd, prefix + ".gamma") * out + x
+
+
 # ----------------------------------------------------------------------------- network
 def backbone(sd, x: torch.Tensor, d: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """reference Backbone.forward, model/backbone.py:50-59 (attention modules = Identity)."""

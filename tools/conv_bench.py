@@ -30,6 +30,9 @@ VARIANTS = {
     "halo_n128": dict(variant=2, ncap=128),
     "halo_n128_m1": dict(variant=2, ncap=128, m=1),
     "halo_n64": dict(variant=2, ncap=64),
+    "halo_bk32": dict(variant=2, bk=32),
+    "halo_bk32_m1": dict(variant=2, bk=32, m=1),
+    "halo_bk16": dict(variant=2, bk=16),
     "halo_noact": dict(variant=2, act=0),        # timing experiments only (results differ by construction)
     "halo_nores": dict(variant=2, nores=1),
 }
@@ -43,6 +46,8 @@ def clone_desc(d: ConvDesc, **kw) -> ConvDesc:
     n.reserved[2] = kw.get("no_station", 0)
     n.reserved[3] = kw.get("ncap", 0)
     n.num_stages = kw.get("stages", 0)
+    if "bk" in kw:
+        n.block_k = kw["bk"]
     if "act" in kw:
         n.act = kw["act"]
     if kw.get("nores"):
@@ -74,7 +79,7 @@ def main():
     rows = []
     totals = {n: 0.0 for n in names}
     for kind, name, payload in eng.ops:
-        if kind != "conv" or (a.filter and a.filter not in name):
+        if kind != "conv" or (a.filter and not any(f in name for f in a.filter.split(","))):
             continue
         dd = payload
         ho, wo = dd.hin // dd.stride, dd.win // dd.stride

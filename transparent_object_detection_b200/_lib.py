@@ -17,7 +17,7 @@ SYMBOLS = (
     "tod_nms_workspace_bytes", "tod_nms", "tod_conv2d_nhwc_bf16_simt_check", "tod_decode_box_from_head",
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
     "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
-    "tod_conv2d_tail1x1_box_decode",
+    "tod_conv2d_tail1x1_box_decode", "tod_cbam_workspace_floats", "tod_cbam_nhwc_bf16",
 )
 
 
@@ -62,6 +62,13 @@ class LetterboxDesc(C.Structure):
         ("xksize", C.c_int32), ("yksize", C.c_int32),
         ("reserved", C.c_int32 * 4),
     ]
+
+
+class CbamDesc(C.Structure):
+    _fields_ = [("d_x", C.c_void_p), ("d_out", C.c_void_p), ("d_fc1", C.c_void_p), ("d_fc2", C.c_void_p),
+                ("d_conv", C.c_void_p), ("d_work", C.c_void_p),
+                ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("hidden", C.c_int32),
+                ("ksize", C.c_int32), ("x_pitch", C.c_int32), ("out_pitch", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class ConvTailDesc(C.Structure):
@@ -115,6 +122,9 @@ def lib() -> C.CDLL:
     L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]
     L.tod_conv2d_tail1x1.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvTailDesc), C.c_void_p]
     L.tod_conv2d_tail1x1_box_decode.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvTailDesc), C.POINTER(HeadFuseDesc), C.c_void_p]
+    L.tod_cbam_workspace_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.tod_cbam_workspace_floats.restype = C.c_int64
+    L.tod_cbam_nhwc_bf16.argtypes = [C.POINTER(CbamDesc), C.c_void_p]
     L.tod_correct_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)  # fail loudly if the binary is stale

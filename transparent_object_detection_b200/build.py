@@ -21,6 +21,7 @@ SOURCES = {
     "stem_u8_tcgen05.cu": [],
     "sppf_pool.cu": [],
     "letterbox.cu": [],
+    "cbam.cu": [],
     "head_decode.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],
 }
