@@ -294,6 +294,17 @@ typedef struct tod_cbam_desc {
 int64_t tod_cbam_workspace_floats(int32_t batch, int32_t h, int32_t w, int32_t c);
 int tod_cbam_nhwc_bf16(const tod_cbam_desc* desc, void* stream);
 
+/*
+ * Row softmax f32 -> bf16.
+ * Replaces: nn.Softmax(dim=-1) over the key axis in SelfAttention.forward  model/blocks.py:246-247.  The block itself is
+ * composed on the host (transparent_object_detection_b200/attention.py) from tod_conv2d_nhwc_bf16 used as a plain
+ * GEMM (q / k projections, q . k^T, (gamma Wv) . x^T, P . v^T + gamma b_v + x) and this kernel: an UNFUSED baseline that
+ * materialises the N x N score matrix per image; a flash-style tcgen05 kernel is the next step.
+ *   d_in f32 [rows, in_pitch] -> d_out bf16 [rows, out_pitch], cols % 4 == 0
+ */
+int tod_softmax_rows_f32_bf16(const float* d_in, void* d_out, int32_t rows, int32_t cols, int64_t in_pitch,
+                              int64_t out_pitch, void* stream);
+
 /* Debug/verification helper used by tests only: direct (non-tensor-core) evaluation of the same conv
  * descriptor on CUDA cores, fp32 accumulate.  Never called by the product path. */
 int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* desc, void* stream);

@@ -12,7 +12,7 @@ import torch
 from oracle import ref_import
 
 CBAM_CASES = [(2, 64, 12, 16), (1, 128, 9, 7), (1, 256, 5, 5), (2, 80, 6, 10)]       # (B, C, H, W); C // 16 hidden channels
-SA_CASES = [(2, 128, 8, 12), (1, 64, 5, 7)]
+SA_CASES = [(2, 128, 8, 12), (1, 64, 4, 12)]                                       # H * W % 16 == 0 (stride-8 maps)
 
 
 def main():

@@ -48,3 +48,81 @@ def test_cbam_in_place_channel_window_and_large_plane():
         ref = O.cbam(sd, "m", keep[..., :C].float().cpu().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     err = (buf[..., :C].float().cpu() - ref).abs()
     assert float((err > 1e-2 * ref.abs() + 1e-2).float().mean()) == 0.0
+
+
+def _sa_bf16_emulation(sd, x):
+    """The oracle's SelfAttention with the build's rounding points: bf16 input, q / k / gamma-scaled v rounded to bf16,
+    f32 scores, bf16 attention weights, f32 accumulation."""
+    import torch.nn.functional as F
+    bf = lambda t: t.to(torch.bfloat16).float()
+    b, c, h, w = x.shape
+    xb = bf(x)
+    q = bf(F.conv2d(xb, bf(sd["query.weight"]), sd["query.bias"])).view(b, -1, h * w).permute(0, 2, 1)
+    k = bf(F.conv2d(xb, bf(sd["key.weight"]), sd["key.bias"])).view(b, -1, h * w)
+    g = float(sd["gamma"])
+    v = bf(F.conv2d(xb, bf(g * sd["value.weight"]), None)).view(b, -1, h * w)
+    att = bf(torch.softmax(torch.bmm(q, k), dim=-1))
+    out = torch.bmm(v, att.permute(0, 2, 1)).view(b, c, h, w)
+    return out + (g * sd["value.bias"]).view(1, -1, 1, 1) + xb
+
+
+def test_self_attention_matches_reference_fixture_and_emulation():
+    """SelfAttention (unfused tcgen05 GEMMs + row softmax) against the fixture written from the reference module (gamma
+    != 0): bf16 q / k move the logits by ~|s| * 2^-8, so the stated tolerance against fp32 is 6e-2 * |ref| + 6e-2; against
+    the emulation with the same rounding points it is 2e-2."""
+    from transparent_object_detection_b200.attention import SelfAttention
+    g = np.load(GOLD)
+    for i, (b, c, h, w) in enumerate(g["sa_cases"]):
+        keys = ("query.weight", "query.bias", "key.weight", "key.bias", "value.weight", "value.bias", "gamma")
+        sd = {k: torch.from_numpy(g[f"sa{i}_{k}"]) for k in keys}
+        m = SelfAttention(int(c))
+        m.load_state_dict(sd)
+        x = torch.from_numpy(g[f"sa{i}_x"])
+        y = m(x.cuda()).cpu()
+        ref = torch.from_numpy(g[f"sa{i}_y"])
+        assert float(((y - ref).abs() > 6e-2 * ref.abs() + 6e-2).float().mean()) <= 2e-3, (i, float((y - ref).abs().max()))
+        emu = _sa_bf16_emulation(sd, x)
+        assert float(((y - emu).abs() > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, (i, float((y - emu).abs().max()))
+        assert float((y - x).abs().max()) > 0.1                      # gamma != 0: the attention term is really there
+
+
+def test_softmax_rows_against_torch():
+    from transparent_object_detection_b200 import lib
+    from transparent_object_detection_b200._lib import check
+    g = torch.Generator().manual_seed(2)
+    for rows, cols, pitch in [(7, 96, 96), (3, 6400, 6400), (5, 48, 64)]:
+        s = (torch.randn((rows, pitch), generator=g) * 6).cuda()
+        o = torch.zeros((rows, pitch), dtype=torch.bfloat16, device="cuda")
+        check(lib().tod_softmax_rows_f32_bf16(s.data_ptr(), o.data_ptr(), rows, cols, pitch, pitch,
+                                              torch.cuda.current_stream().cuda_stream), "softmax")
+        torch.cuda.synchronize()
+        want = torch.softmax(s[:, :cols], -1)
+        err = (o[:, :cols].float() - want).abs()
+        assert float((err > 1e-2 * want + 1e-6).float().mean()) == 0.0
+        assert abs(float(o[:, :cols].float().sum(1).mean()) - 1.0) < 5e-3
+
+
+def test_self_attention_at_network_size():
+    """The backbone's instance at scale s, 640x640 (model/backbone.py:33): C = 128 on the 80x80 map, N = 6400 tokens, one
+    image; against the emulation with the same rounding points (f32 scores are 164 MB, bf16 weights 82 MB per image)."""
+    from transparent_object_detection_b200.attention import SelfAttention
+    g = torch.Generator().manual_seed(8)
+    c, h, w = 128, 80, 80
+    m = SelfAttention(c)
+    sd = {"query.weight": torch.randn((16, c, 1, 1), generator=g) * 0.08, "query.bias": torch.randn((16,), generator=g) * 0.1,
+          "key.weight": torch.randn((16, c, 1, 1), generator=g) * 0.08, "key.bias": torch.randn((16,), generator=g) * 0.1,
+          "value.weight": torch.randn((c, c, 1, 1), generator=g) * 0.1, "value.bias": torch.randn((c,), generator=g) * 0.1,
+          "gamma": torch.tensor([0.5])}
+    m.load_state_dict(sd)
+    x = torch.randn((1, c, h, w), generator=g)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xc = x.cuda()
+    m(xc)                                   # warm-up (function attributes, module loading)
+    e0.record()
+    y = m(xc)
+    e1.record()
+    torch.cuda.synchronize()
+    emu = _sa_bf16_emulation(sd, x)
+    err = (y.cpu() - emu).abs()
+    assert float((err > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, float(err.max())
+    print(f"SelfAttention 1 x 128 x 80 x 80 (N = 6400), layout conversions included: {e0.elapsed_time(e1):.2f} ms")

@@ -51,3 +51,90 @@ class CBAM(nn.Module):
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         y = cbam_nhwc(xn, f32(self.fc1.weight.flatten(1)), f32(self.fc2.weight.flatten(1)), f32(self.conv.weight[0]))
         return y.permute(0, 3, 1, 2).to(x.dtype).to(x.device)
+
+
+# ----------------------------------------------------------------------------------------------- SelfAttention
+def _gemm(L, st, x_ptr, h, w, cin, x_pitch, w_ptr, cout, out_ptr, out_pitch, out_f32=False, bias_ptr=None,
+          res_ptr=None, res_pitch=0, what="gemm"):
+    """D[h*w, cout] = A[h*w, cin] . W[cout, cin]^T (+ bias) (+ residual) through tod_conv2d_nhwc_bf16 as a 1x1 conv."""
+    from ._lib import ConvDesc, TOD_ACT_NONE, TOD_OUT_BF16, TOD_OUT_F32
+    d = ConvDesc()
+    d.d_x, d.d_w, d.d_out = x_ptr, w_ptr, out_ptr
+    d.d_bias, d.d_residual = bias_ptr, res_ptr
+    d.batch, d.hin, d.win, d.cin, d.cout, d.ksize, d.stride = 1, h, w, cin, cout, 1, 1
+    d.x_pitch, d.out_pitch, d.res_pitch = x_pitch, out_pitch, res_pitch
+    d.act, d.out_dtype = TOD_ACT_NONE, (TOD_OUT_F32 if out_f32 else TOD_OUT_BF16)
+    check(L.tod_conv2d_nhwc_bf16(C.byref(d), st), what)
+
+
+def self_attention_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: float) -> torch.Tensor:
+    """reference SelfAttention.forward (model/blocks.py:236-254) on a dense NHWC bf16 CUDA tensor (B, H, W, C), H * W % 16
+    == 0.  UNFUSED baseline: per image the N x N scores are materialised (f32), soft-maxed into bf16 weights and applied
+    with a second GEMM; every GEMM is the tcgen05 conv kernel used as a 1x1 conv:
+        q, k = x Wq^T + bq, x Wk^T + bk                (output channels zero-padded to a multiple of 16)
+        S    = q k^T                                   (A = q_i, "weights" = k_i: its NHWC rows are already [N, d] K-major)
+        P    = softmax_rows(S)                         (tod_softmax_rows_f32_bf16)
+        vT   = (gamma Wv) x_i^T                        (A = gamma Wv, "weights" = x_i) -> [C, N], K-major for the last GEMM
+        out  = P vT^T + gamma bv + x_i                 (softmax rows sum to one, so the value bias moves out of the sum)"""
+    from .engine import pack_conv_weight
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()):
+        raise ValueError("x must be a contiguous bf16 CUDA tensor (B, H, W, C)")
+    B, H, W, Cc = x.shape
+    N = H * W
+    if N % 16 or Cc % 16:
+        raise ValueError(f"SelfAttention needs H * W and C to be multiples of 16 (got {H}x{W}, C = {Cc})")
+    dev = x.device
+    L = lib()
+    d = wq.shape[0]
+    d16 = (d + 15) // 16 * 16
+
+    def padded(wt, bs):
+        wp = torch.zeros((d16, Cc, 1, 1), dtype=torch.float32)
+        bp = torch.zeros((d16,), dtype=torch.float32)
+        wp[:d] = wt.detach().float().cpu().reshape(d, Cc, 1, 1)
+        bp[:d] = bs.detach().float().cpu()
+        return pack_conv_weight(wp).to(dev), bp.to(dev)
+
+    wq_p, bq_p = padded(wq, bq)
+    wk_p, bk_p = padded(wk, bk)
+    wv_g = (float(gamma) * wv.detach().float().cpu().reshape(Cc, Cc)).to(torch.bfloat16).to(dev).contiguous()   # A operand [C, C_in]
+    bv_g = (float(gamma) * bv.detach().float().cpu()).to(dev).contiguous()
+    q = torch.empty((B, H, W, d16), dtype=torch.bfloat16, device=dev)
+    k = torch.empty_like(q)
+    out = torch.empty_like(x)
+    S = torch.empty((N, N), dtype=torch.float32, device=dev)
+    P = torch.empty((N, N), dtype=torch.bfloat16, device=dev)
+    vT = torch.empty((Cc, N), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for i in range(B):
+            xi = x.data_ptr() + i * N * Cc * 2
+            qi, ki = q.data_ptr() + i * N * d16 * 2, k.data_ptr() + i * N * d16 * 2
+            _gemm(L, st, xi, H, W, Cc, Cc, wq_p.data_ptr(), d16, qi, d16, bias_ptr=bq_p.data_ptr(), what="query")
+            _gemm(L, st, xi, H, W, Cc, Cc, wk_p.data_ptr(), d16, ki, d16, bias_ptr=bk_p.data_ptr(), what="key")
+            _gemm(L, st, qi, H, W, d16, d16, ki, N, S.data_ptr(), N, out_f32=True, what="scores")
+            check(L.tod_softmax_rows_f32_bf16(S.data_ptr(), P.data_ptr(), N, N, N, N, st), "softmax")
+            _gemm(L, st, wv_g.data_ptr(), 1, Cc, Cc, Cc, xi, N, vT.data_ptr(), N, what="value^T")
+            _gemm(L, st, P.data_ptr(), H, W, N, N, vT.data_ptr(), Cc, out.data_ptr() + i * N * Cc * 2, Cc,
+                  bias_ptr=bv_g.data_ptr(), res_ptr=xi, res_pitch=Cc, what="attention output")
+        torch.cuda.current_stream(dev).synchronize()      # the temporaries above are freed on return
+    return out
+
+
+class SelfAttention(nn.Module):
+    """reference SelfAttention (model/blocks.py:226-254): same constructor and parameter names (query, key, value, gamma),
+    forward on the reference's NCHW float tensor."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.query = nn.Conv2d(channels, channels // 8, kernel_size=1)
+        self.key = nn.Conv2d(channels, channels // 8, kernel_size=1)
+        self.value = nn.Conv2d(channels, channels, kernel_size=1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        xn = x.to(dev).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        y = self_attention_nhwc(xn, self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight,
+                                self.value.bias, float(self.gamma.detach()))
+        return y.permute(0, 3, 1, 2).to(x.dtype).to(x.device)

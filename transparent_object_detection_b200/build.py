@@ -22,6 +22,7 @@ SOURCES = {
     "sppf_pool.cu": [],
     "letterbox.cu": [],
     "cbam.cu": [],
+    "softmax.cu": [],
     "head_decode.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],
 }
