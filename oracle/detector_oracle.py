@@ -134,13 +134,21 @@ def self_attention(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- network
-def backbone(sd, x: torch.Tensor, d: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """reference Backbone.forward, model/backbone.py:50-59 (attention modules = Identity)."""
+def backbone(sd, x: torch.Tensor, d: int, attention: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """reference Backbone.forward, model/backbone.py:50-59.  attention=False: the plain topology (attention modules =
+    Identity); attention=True: the current source with CBAM after dark2 / dark4's C2f and SelfAttention after
+    dark3's (:26,33,40)."""
     x = conv_bn_silu(sd, "backbone.stem", x, 2)
     x = c2f(sd, "backbone.dark2.1", conv_bn_silu(sd, "backbone.dark2.0", x, 2), d, True)
+    if attention:
+        x = cbam(sd, "backbone.dark2.2", x)
     x = c2f(sd, "backbone.dark3.1", conv_bn_silu(sd, "backbone.dark3.0", x, 2), 2 * d, True)
+    if attention:
+        x = self_attention(sd, "backbone.dark3.2", x)
     feat1 = x
     x = c2f(sd, "backbone.dark4.1", conv_bn_silu(sd, "backbone.dark4.0", x, 2), 2 * d, True)
+    if attention:
+        x = cbam(sd, "backbone.dark4.2", x)
     feat2 = x
     x = c2f(sd, "backbone.dark5.1", conv_bn_silu(sd, "backbone.dark5.0", x, 2), d, True)
     feat3 = sppf(sd, "backbone.dark5.2", x)
@@ -158,14 +166,20 @@ def neck(sd, feats: Sequence[torch.Tensor], d: int) -> Tuple[torch.Tensor, torch
     return h2, h4, h6
 
 
-def head_raw(sd, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    """reference Head.forward up to the training-mode return, model/head.py:46-51: cat(box, cls) per level."""
+def head_raw(sd, feats: Sequence[torch.Tensor], attention: bool = False) -> List[torch.Tensor]:
+    """reference Head.forward up to the training-mode return, model/head.py:46-51: cat(box, cls) per level; attention=True:
+    the current source's CBAM after each of the two Convs of a tower (:28,30,39,41)."""
     out = []
     for i, x in enumerate(feats):
         t = []
         for name in ("box", "cls"):
             p = f"head.{name}.{i}"
-            y = conv_bn_silu(sd, p + ".2", conv_bn_silu(sd, p + ".0", x))
+            y = conv_bn_silu(sd, p + ".0", x)
+            if attention:
+                y = cbam(sd, p + ".1", y)
+            y = conv_bn_silu(sd, p + ".2", y)
+            if attention:
+                y = cbam(sd, p + ".3", y)
             t.append(F.conv2d(y, _t(sd, p + ".4.weight"), _t(sd, p + ".4.bias")))
         out.append(torch.cat(t, 1))
     return out
@@ -205,9 +219,11 @@ def head_decode(raw: Sequence[torch.Tensor], nc: int, strides: Sequence[float] =
     return torch.cat((box * st, cls.sigmoid()), 1)
 
 
-def forward(sd, x: torch.Tensor, nc: int, d: int, training: bool = False):
-    """reference BaseModel.forward, model/base.py:18-24 (head.stride = 8,16,32 per SURVEY F6)."""
-    raw = head_raw(sd, neck(sd, backbone(sd, x, d), d))
+def forward(sd, x: torch.Tensor, nc: int, d: int, training: bool = False, attention: bool = False):
+    """reference BaseModel.forward, model/base.py:18-24 (head.stride = 8,16,32 per SURVEY F6).  attention=True: the
+    current-source backbone and head (CBAM / SelfAttention) around the plain neck (the current-source neck does not run:
+    SURVEY F3)."""
+    raw = head_raw(sd, neck(sd, backbone(sd, x, d, attention), d), attention)
     return raw if training else head_decode(raw, nc)
 
 

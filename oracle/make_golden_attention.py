@@ -48,3 +48,24 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def network_fixture():
+    """Scale n with the CURRENT-SOURCE backbone and head (CBAM x 14, SelfAttention) around the plain neck, 2 x 3 x 64 x 96:
+    stage features and the eval head tensor of the reference itself -> tests/golden/net_n_attention_64x96.npz."""
+    from oracle import synth
+    C, d, m = synth.SCALES["n"]
+    sd = synth.make_state_dict(80, C, d, m, seed=0)
+    sd.update(synth.make_attention_state_dict(80, C, d, m, seed=0))
+    model = ref_import.build_reference_model(80, C, d, m, sd, attention=True)
+    x = torch.from_numpy(synth.make_images(2, 64, 96, seed=7))
+    with torch.no_grad():
+        p3, p4, p5 = model.backbone(x)
+        out = model(x)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "net_n_attention_64x96.npz")
+    np.savez_compressed(path, p3=p3.numpy(), p4=p4.numpy(), p5=p5.numpy(), out=out.numpy())
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    network_fixture()

@@ -59,7 +59,7 @@ def import_reference():
     return ref_model, ref_bbox
 
 
-def build_reference_model(nc: int, C: int, d: int, deep_mul: float, state_dict=None):
+def build_reference_model(nc: int, C: int, d: int, deep_mul: float, state_dict=None, attention: bool = False):
     """Patched-current-source reference BaseModel in eval mode (network-level oracle)."""
     import torch
     import torch.nn as nn
@@ -67,16 +67,18 @@ def build_reference_model(nc: int, C: int, d: int, deep_mul: float, state_dict=N
     from model.blocks import C2f
     m = ref_model.BaseModel(nc, C, d, deep_mul)
     C5 = int(C * 16 * deep_mul)
-    for name in ("dark2", "dark3", "dark4"):
-        getattr(m.backbone, name)[2] = nn.Identity()
+    if not attention:          # attention=True keeps the current source's CBAM / SelfAttention modules
+        for name in ("dark2", "dark3", "dark4"):
+            getattr(m.backbone, name)[2] = nn.Identity()
     m.neck.h1 = C2f(C5 + 8 * C, 8 * C, d, False)
     m.neck.h2 = C2f(8 * C + 4 * C, 4 * C, d, False)
     m.neck.h4 = C2f(8 * C + 4 * C, 8 * C, d, False)
     m.neck.h6 = C2f(C5 + 8 * C, C5, d, False)
-    for tower in (m.head.cls, m.head.box):
-        for seq in tower:
-            seq[1] = nn.Identity()
-            seq[3] = nn.Identity()
+    if not attention:
+        for tower in (m.head.cls, m.head.box):
+            for seq in tower:
+                seq[1] = nn.Identity()
+                seq[3] = nn.Identity()
     m.head.stride = torch.tensor([8.0, 16.0, 32.0])
     if state_dict is not None:
         sd = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(v.copy()) if v.shape else torch.tensor(v))

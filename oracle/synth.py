@@ -48,6 +48,49 @@ def _c2f_keys(table, prefix, c1, c2, n):
         _conv_keys(table, f"{prefix}.m.{j}.cv2", c, c, 3)
 
 
+def _cbam_keys(table, prefix, c):
+    """reference CBAM (model/blocks.py:192-204): fc1, fc2 (1x1, no bias, reduction 16), conv (2 -> 1, 7x7, no bias)."""
+    table[prefix + ".fc1.weight"] = (c // 16, c, 1, 1)
+    table[prefix + ".fc2.weight"] = (c, c // 16, 1, 1)
+    table[prefix + ".conv.weight"] = (1, 2, 7, 7)
+
+
+def attention_shapes(nc: int, C: int, d: int, deep_mul: float) -> "OrderedDict[str, tuple]":
+    """Extra keys of the CURRENT-SOURCE backbone / head (model/backbone.py:26,33,40, model/head.py:28,30,39,41)."""
+    t: "OrderedDict[str, tuple]" = OrderedDict()
+    _cbam_keys(t, "backbone.dark2.2", 2 * C)
+    c = 4 * C
+    for name, co in (("query", c // 8), ("key", c // 8), ("value", c)):
+        t[f"backbone.dark3.2.{name}.weight"] = (co, c, 1, 1)
+        t[f"backbone.dark3.2.{name}.bias"] = (co,)
+    t["backbone.dark3.2.gamma"] = (1,)
+    _cbam_keys(t, "backbone.dark4.2", 8 * C)
+    c1, c2 = max(4 * C, nc), max(4 * C // 4, 64)
+    for name, cm in (("cls", c1), ("box", c2)):
+        for i in range(3):
+            _cbam_keys(t, f"head.{name}.{i}.1", cm)
+            _cbam_keys(t, f"head.{name}.{i}.3", cm)
+    return t
+
+
+def make_attention_state_dict(nc: int, C: int, d: int, deep_mul: float, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Weights of the attention blocks: N(0, sqrt(2 / fan_in)) convs, small biases, gamma = 0.5 (the reference's zero
+    initialisation would switch the SelfAttention term off: SURVEY F10)."""
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for key, shape in attention_shapes(nc, C, d, deep_mul).items():
+        r = _rng(seed, key)
+        if key.endswith("gamma"):
+            v = np.full(shape, 0.5, np.float32)
+        elif key.endswith("bias"):
+            v = (0.1 * r.standard_normal(shape)).astype(np.float32)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3]
+            scale = np.sqrt(2.0 / fan_in) * (0.5 if ".query." in key or ".key." in key else 1.0)
+            v = (r.standard_normal(shape) * scale).astype(np.float32)
+        out[key] = v
+    return out
+
+
 def state_dict_shapes(nc: int, C: int, d: int, deep_mul: float) -> "OrderedDict[str, tuple]":
     """Key -> shape for the plain-topology detector, in reference module order."""
     C5 = int(C * 16 * deep_mul)

@@ -31,3 +31,28 @@ def test_self_attention_oracle_matches_reference_fixture():
         with torch.no_grad():
             y = O.self_attention(sd, "m", torch.from_numpy(g[f"sa{i}_x"]))
         np.testing.assert_allclose(y.numpy(), g[f"sa{i}_y"], rtol=1e-5, atol=1e-5)
+
+
+def test_current_source_network_oracle_matches_reference_fixture():
+    from oracle import synth
+    g = np.load(os.path.join(os.path.dirname(GOLD), "net_n_attention_64x96.npz"))
+    C_, d, m = synth.SCALES["n"]
+    sd = synth.make_state_dict(80, C_, d, m, seed=0)
+    sd.update(synth.make_attention_state_dict(80, C_, d, m, seed=0))
+    x = torch.from_numpy(synth.make_images(2, 64, 96, seed=7))
+    with torch.no_grad():
+        feats = O.backbone(sd, x, d, attention=True)
+        out = O.forward(sd, x, 80, d, attention=True)
+    for name, t in zip(("p3", "p4", "p5"), feats):
+        np.testing.assert_allclose(t.numpy(), g[name], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-4, atol=1e-4)
+
+
+def test_attention_parameter_table_matches_the_state_dict_layout():
+    from oracle import synth
+    from transparent_object_detection_b200.model import attention_parameter_table
+    for scale in ("n", "s", "m"):
+        C_, d, m = synth.SCALES[scale]
+        want = synth.attention_shapes(80, C_, d, m)
+        got = {k: tuple(s) for k, s, _ in attention_parameter_table(80, C_, d, m)}
+        assert got == {k: tuple(v) for k, v in want.items()}

@@ -126,3 +126,42 @@ def test_self_attention_at_network_size():
     err = (y.cpu() - emu).abs()
     assert float((err > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, float(err.max())
     print(f"SelfAttention 1 x 128 x 80 x 80 (N = 6400), layout conversions included: {e0.elapsed_time(e1):.2f} ms")
+
+
+def test_current_source_network_matches_reference_fixture():
+    """BaseModel(..., attention=True): the CURRENT-SOURCE backbone and head (2 + 12 CBAM, 1 SelfAttention with gamma = 0.5)
+    around the plain neck, scale n, 2 x 3 x 64 x 96, against the reference's own modules (fixture written by
+    oracle/make_golden_attention.py): stage features within 4 % of abs-max, boxes <= 1.5 px, scores <= 8e-3; the captured
+    graph (Detector) gives the rows of the oracle's NMS on the eager decoded tensor."""
+    from oracle import detector_oracle as O, synth
+    from transparent_object_detection_b200 import BaseModel, DecodeBox, Detector
+    g = np.load(os.path.join(os.path.dirname(GOLD), "net_n_attention_64x96.npz"))
+    C_, d, m = synth.SCALES["n"]
+    sd = synth.make_state_dict(80, C_, d, m, seed=0)
+    sd.update(synth.make_attention_state_dict(80, C_, d, m, seed=0))
+    model = BaseModel(80, C_, d, m, attention=True).eval()
+    missing = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    x = torch.from_numpy(synth.make_images(2, 64, 96, seed=7))
+    out = model(x.cuda()).cpu()
+    eng = model.engine(2, 64, 96, torch.device("cuda", torch.cuda.current_device()))
+    assert sum(1 for k, _, _ in eng.ops if k == "cbam") == 14 and sum(1 for k, _, _ in eng.ops if k == "attn") == 1
+    for name in ("p3", "p4", "p5"):
+        ref = torch.from_numpy(g[name])
+        err = (eng.feature_nchw(name).cpu() - ref).abs()
+        assert float(err.max()) <= 0.04 * float(ref.abs().max()), (name, float(err.max()), float(ref.abs().max()))
+    want = torch.from_numpy(g["out"])
+    assert float((out[:, :4] - want[:, :4]).abs().max()) <= 1.5
+    assert float((out[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+    # and it differs from the plain topology (the attention blocks are really in the path)
+    plain = BaseModel(80, C_, d, m).eval()
+    plain.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    assert float((plain(x.cuda()).cpu() - out).abs().max()) > 0.5
+    db = DecodeBox(80, (64, 96))
+    dec = db.decode_box(model(x.cuda()))
+    conf = float(dec[:, :, 4:].max()) * 0.5
+    want_rows = O.non_max_suppression(dec.cpu().numpy().copy(), 80, (64, 96), (64, 96), True, conf, 0.5)
+    got_rows = Detector(model, (64, 96), confidence=conf, nms_iou=0.5).detect(x)
+    assert any(r is not None for r in want_rows)
+    for a, b in zip(got_rows, want_rows):
+        assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))

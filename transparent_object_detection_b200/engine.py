@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, ConvTailDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16,
+from ._lib import (CbamDesc, ConvDesc, ConvTailDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16,
                    TOD_OUT_F32, check)
 
 BN_EPS = 1e-5
@@ -89,7 +89,7 @@ class DetectorEngine:
     """Fixed-shape plan: (batch, 3, in_h, in_w) float32 NCHW in -> raw maps / head tensor / detections."""
 
     def __init__(self, state_dict, num_classes: int, base_channels: int, base_depth: int, deep_mul: float,
-                 batch: int, in_h: int, in_w: int, device: Optional[torch.device] = None):
+                 batch: int, in_h: int, in_w: int, device: Optional[torch.device] = None, attention: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("transparent_object_detection_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.L = _lib.lib()
@@ -103,6 +103,7 @@ class DetectorEngine:
         self.nc, self.C, self.d, self.deep_mul = num_classes, base_channels, base_depth, deep_mul
         self.C5 = int(base_channels * 16 * deep_mul)
         self.batch, self.in_h, self.in_w = batch, in_h, in_w
+        self.attention = bool(attention)   # current-source backbone / head: CBAM and SelfAttention ops in the plan
         self.ops: List[Tuple[str, str, object]] = []   # (kind, name, payload)
         self._keep: List[torch.Tensor] = []            # weights / biases / activation arena kept alive
         self.conv_flops = 0
@@ -152,6 +153,62 @@ class DetectorEngine:
                                     out_f32=out_f32)
         self.conv_flops += 2 * self.batch * dst.h * dst.w * cout * cin * k * k
 
+    def _cbam(self, sd, prefix: str, v: View) -> None:
+        """reference CBAM (model/blocks.py:206-223) in place on a channel view (tod_cbam_nhwc_bf16)."""
+        fc1 = self._dev(_t(sd, prefix + ".fc1.weight").float().flatten(1))
+        fc2 = self._dev(_t(sd, prefix + ".fc2.weight").float().flatten(1))
+        cw = self._dev(_t(sd, prefix + ".conv.weight").float()[0])
+        work = torch.zeros(int(self.L.tod_cbam_workspace_floats(self.batch, v.h, v.w, v.c)), dtype=torch.float32, device=self.device)
+        self._keep.append(work)
+        d = CbamDesc()
+        d.d_x, d.d_out, d.d_work = v.ptr, v.ptr, work.data_ptr()
+        d.d_fc1, d.d_fc2, d.d_conv = fc1.data_ptr(), fc2.data_ptr(), cw.data_ptr()
+        d.batch, d.h, d.w, d.c, d.hidden, d.ksize = self.batch, v.h, v.w, v.c, fc1.shape[0], cw.shape[-1]
+        d.x_pitch, d.out_pitch = v.pitch, v.pitch
+        self.ops.append(("cbam", prefix, d))
+
+    def _self_attention(self, sd, prefix: str, v: View) -> None:
+        """reference SelfAttention (model/blocks.py:236-254) in place on a dense map: the unfused GEMM chain of
+        attention.self_attention_nhwc with every operand and temporary allocated once (graph-capturable)."""
+        assert v.pitch == v.c and v.c_off == 0, "SelfAttention needs a dense buffer"
+        Cc, N = v.c, v.h * v.w
+        assert N % 16 == 0 and Cc % 16 == 0, (N, Cc)
+        wq, wk = _t(sd, prefix + ".query.weight").float(), _t(sd, prefix + ".key.weight").float()
+        dq = wq.shape[0]
+        d16 = (dq + 15) // 16 * 16
+        gamma = float(_t(sd, prefix + ".gamma").reshape(-1)[0])
+
+        def padded(wt, bs):
+            wp, bp = torch.zeros((d16, Cc, 1, 1)), torch.zeros((d16,))
+            wp[:dq], bp[:dq] = wt.reshape(dq, Cc, 1, 1), bs.float()
+            return self._dev(pack_conv_weight(wp)), self._dev(bp)
+
+        plan = dict(v=v, N=N, C=Cc, d16=d16)
+        plan["wq"], plan["bq"] = padded(wq, _t(sd, prefix + ".query.bias"))
+        plan["wk"], plan["bk"] = padded(wk, _t(sd, prefix + ".key.bias"))
+        plan["wv"] = self._dev((gamma * _t(sd, prefix + ".value.weight").float().reshape(Cc, Cc)).to(torch.bfloat16))
+        plan["bv"] = self._dev(gamma * _t(sd, prefix + ".value.bias").float())
+        for name, shape, dt in (("q", (self.batch, N, d16), torch.bfloat16), ("k", (self.batch, N, d16), torch.bfloat16),
+                                ("S", (N, N), torch.float32), ("P", (N, N), torch.bfloat16), ("vT", (Cc, N), torch.bfloat16)):
+            plan[name] = torch.zeros(shape, dtype=dt, device=self.device)
+            self._keep.append(plan[name])
+        self.ops.append(("attn", prefix, plan))
+        self.conv_flops += 2 * self.batch * (2 * N * d16 * Cc + N * N * d16 + N * Cc * Cc + N * N * Cc)
+
+    def _run_attention(self, plan: dict, st: int) -> None:
+        from .attention import _gemm
+        L, v, N, Cc, d16 = self.L, plan["v"], plan["N"], plan["C"], plan["d16"]
+        for i in range(self.batch):
+            xi = v.ptr + i * N * Cc * 2
+            qi, ki = plan["q"].data_ptr() + i * N * d16 * 2, plan["k"].data_ptr() + i * N * d16 * 2
+            _gemm(L, st, xi, v.h, v.w, Cc, Cc, plan["wq"].data_ptr(), d16, qi, d16, bias_ptr=plan["bq"].data_ptr(), what="query")
+            _gemm(L, st, xi, v.h, v.w, Cc, Cc, plan["wk"].data_ptr(), d16, ki, d16, bias_ptr=plan["bk"].data_ptr(), what="key")
+            _gemm(L, st, qi, v.h, v.w, d16, d16, ki, N, plan["S"].data_ptr(), N, out_f32=True, what="scores")
+            check(L.tod_softmax_rows_f32_bf16(plan["S"].data_ptr(), plan["P"].data_ptr(), N, N, N, N, st), "softmax")
+            _gemm(L, st, plan["wv"].data_ptr(), 1, Cc, Cc, Cc, xi, N, plan["vT"].data_ptr(), N, what="value^T")
+            _gemm(L, st, plan["P"].data_ptr(), v.h, v.w, N, N, plan["vT"].data_ptr(), Cc, xi, Cc,
+                  bias_ptr=plan["bv"].data_ptr(), res_ptr=xi, res_pitch=Cc, what="attention output")
+
     def _conv_bn(self, sd, prefix: str, src: View, dst: View, stride: int = 1, residual: Optional[View] = None) -> None:
         w, b = fold_conv_bn(sd, prefix)
         self._conv(prefix, w, b, src, dst, stride, TOD_ACT_SILU, residual)
@@ -196,14 +253,20 @@ class DetectorEngine:
         self._conv_bn(sd, "backbone.dark2.0", stem, d2, 2)
         d2o = self._buf(H // 4, W // 4, 2 * C)
         self._c2f(sd, "backbone.dark2.1", d2, d2o, d, True)
+        if self.attention:
+            self._cbam(sd, "backbone.dark2.2", d2o)
         d3 = self._buf(H // 8, W // 8, 4 * C)
         self._conv_bn(sd, "backbone.dark3.0", d2o, d3, 2)
         p3 = self._buf(H // 8, W // 8, 4 * C)
         self._c2f(sd, "backbone.dark3.1", d3, p3, 2 * d, True)
+        if self.attention:
+            self._self_attention(sd, "backbone.dark3.2", p3)
         d4 = self._buf(H // 16, W // 16, 8 * C)
         self._conv_bn(sd, "backbone.dark4.0", p3, d4, 2)
         p4 = self._buf(H // 16, W // 16, 8 * C)
         self._c2f(sd, "backbone.dark4.1", d4, p4, 2 * d, True)
+        if self.attention:
+            self._cbam(sd, "backbone.dark4.2", p4)
         d5 = self._buf(H // 32, W // 32, C5)
         self._conv_bn(sd, "backbone.dark5.0", p4, d5, 2)
         d5o = self._buf(H // 32, W // 32, C5)
@@ -243,12 +306,20 @@ class DetectorEngine:
             rv = View(raw, 0, self.raw_pitch)
             tb1, tb2 = self._buf(f.h, f.w, c2), self._buf(f.h, f.w, c2)
             self._conv_bn(sd, f"head.box.{i}.0", f, tb1)
+            if self.attention:
+                self._cbam(sd, f"head.box.{i}.1", tb1)
             self._conv_bn(sd, f"head.box.{i}.2", tb1, tb2)
+            if self.attention:
+                self._cbam(sd, f"head.box.{i}.3", tb2)
             self._conv(f"head.box.{i}.4", _t(sd, f"head.box.{i}.4.weight"), _t(sd, f"head.box.{i}.4.bias"), tb2,
                        rv.sub(0, 64), act=TOD_ACT_NONE, out_f32=True)
             tc1, tc2 = self._buf(f.h, f.w, c1), self._buf(f.h, f.w, c1)
             self._conv_bn(sd, f"head.cls.{i}.0", f, tc1)
+            if self.attention:
+                self._cbam(sd, f"head.cls.{i}.1", tc1)
             self._conv_bn(sd, f"head.cls.{i}.2", tc1, tc2)
+            if self.attention:
+                self._cbam(sd, f"head.cls.{i}.3", tc2)
             wc = torch.zeros(ncp, c1, 1, 1)
             bc = torch.zeros(ncp)
             wc[:nc] = _t(sd, f"head.cls.{i}.4.weight")
@@ -301,7 +372,7 @@ class DetectorEngine:
         # conv + DFL / dist2bbox in one kernel per level (model/head.py:36-42,53-61)
         self.tail_box: Dict[str, Tuple[ConvTailDesc, HeadFuseDesc]] = {}
         self.tail_box_skip = set()
-        if os.environ.get("TOD_FUSE_TAIL", "1") != "0":
+        if os.environ.get("TOD_FUSE_TAIL", "1") != "0" and not self.attention:   # (a CBAM sits between .2 and .4 otherwise)
             for i in range(len(self.level_shapes)):
                 na, nb = f"head.box.{i}.2", f"head.box.{i}.4"
                 a, b_ = self.conv_meta[na], self.conv_meta[nb]
@@ -372,6 +443,10 @@ class DetectorEngine:
             elif kind == "pool":
                 buf, c_ = payload
                 check(L.tod_sppf_pool_nhwc_bf16(buf.ptr, self.batch, buf.h, buf.w, c_, buf.pitch, st), name)
+            elif kind == "cbam":
+                check(L.tod_cbam_nhwc_bf16(C.byref(payload), st), name)
+            elif kind == "attn":
+                self._run_attention(payload, st)
             else:  # pragma: no cover
                 raise AssertionError(kind)
 
@@ -431,7 +506,8 @@ class DetectorEngine:
     # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
     @property
     def launches_per_pass(self) -> int:
-        return (len(self.ops) - len(self.tail_skip) - (len(self.tail_box_skip) if self.fuse_head_decode else 0)
+        extra = sum(3 if k == "cbam" else (6 * self.batch - 1 if k == "attn" else 0) for k, _, _ in self.ops)
+        return (len(self.ops) + extra - len(self.tail_skip) - (len(self.tail_box_skip) if self.fuse_head_decode else 0)
                 + (0 if self.fuse_head_decode else 1) + 3)
 
     def capture(self, conf_thres: float, nms_thres: float, head_out: bool = False, decoded: bool = False) -> None:

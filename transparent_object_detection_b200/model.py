@@ -42,6 +42,27 @@ def _c2f_entries(prefix: str, c1: int, c2: int, n: int):
     return e
 
 
+def _cbam_entries(prefix: str, c: int):
+    """reference CBAM (model/blocks.py:192-204)."""
+    return [(prefix + ".fc1.weight", (c // 16, c, 1, 1), "param"), (prefix + ".fc2.weight", (c, c // 16, 1, 1), "param"),
+            (prefix + ".conv.weight", (1, 2, 7, 7), "param")]
+
+
+def attention_parameter_table(nc: int, C: int, d: int, deep_mul: float):
+    """Extra parameters of the CURRENT-SOURCE backbone / head (model/backbone.py:26,33,40; model/head.py:28,30,39,41)."""
+    c = 4 * C
+    e = _cbam_entries("backbone.dark2.2", 2 * C)
+    for name, co in (("query", c // 8), ("key", c // 8), ("value", c)):
+        e += [(f"backbone.dark3.2.{name}.weight", (co, c, 1, 1), "param"), (f"backbone.dark3.2.{name}.bias", (co,), "param")]
+    e.append(("backbone.dark3.2.gamma", (1,), "param"))
+    e += _cbam_entries("backbone.dark4.2", 8 * C)
+    c1, c2 = max(4 * C, nc), max(4 * C // 4, 64)
+    for name, cm in (("cls", c1), ("box", c2)):
+        for i in range(3):
+            e += _cbam_entries(f"head.{name}.{i}.1", cm) + _cbam_entries(f"head.{name}.{i}.3", cm)
+    return e
+
+
 def parameter_table(nc: int, C: int, d: int, deep_mul: float):
     """(key, shape, kind) in the reference's registration order (backbone.py:20-48, neck.py:19-53 with C2f
     stages per SURVEY F4, head.py:19-44 with Sequential indices 0/2/4)."""
@@ -82,12 +103,19 @@ class BaseModel(nn.Module):
       train -> list of three raw maps (B, 64+nc, h, w)                              (model/head.py:50-51)
     """
 
-    def __init__(self, num_classes: int, base_channels: int, base_depth: int, deep_mul: float):
+    def __init__(self, num_classes: int, base_channels: int, base_depth: int, deep_mul: float, attention: bool = False):
+        """attention=True: the CURRENT-SOURCE backbone and head -- CBAM after dark2 / dark4 and after both Convs of every
+        head tower, SelfAttention after dark3 (model/backbone.py:26,33,40; model/head.py:28,30,39,41) --
+        with the reference's parameter names, around the plain neck (the current-source neck does not run: SURVEY F3)."""
         super().__init__()
         self.num_classes, self.base_channels, self.base_depth, self.deep_mul = num_classes, base_channels, base_depth, deep_mul
+        self.attention = bool(attention)
         for root in ("backbone", "neck", "head"):
             self.add_module(root, _Node())
-        for key, shape, kind in parameter_table(num_classes, base_channels, base_depth, deep_mul):
+        table = parameter_table(num_classes, base_channels, base_depth, deep_mul)
+        if self.attention:
+            table = table + attention_parameter_table(num_classes, base_channels, base_depth, deep_mul)
+        for key, shape, kind in table:
             root, *path, leaf = key.split(".")
             node = self._modules[root]
             for p in path:
@@ -101,7 +129,7 @@ class BaseModel(nn.Module):
                     init = torch.arange(16, dtype=torch.float32).view(shape)           # model/blocks.py:150-152
                 elif leaf == "weight" and len(shape) == 1:
                     init = torch.ones(shape)
-                elif leaf == "bias":
+                elif leaf == "bias" or leaf == "gamma":              # gamma = 0 like model/blocks.py:233
                     init = torch.zeros(shape)
                 else:
                     fan_in = shape[1] * shape[2] * shape[3]
@@ -126,7 +154,7 @@ class BaseModel(nn.Module):
         eng = self._engines.get(key)
         if eng is None:
             eng = DetectorEngine(self.state_dict(), self.num_classes, self.base_channels, self.base_depth,
-                                 self.deep_mul, batch, in_h, in_w, device)
+                                 self.deep_mul, batch, in_h, in_w, device, attention=self.attention)
             self._engines[key] = eng
         return eng
 
