@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--ref-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attention", action="store_true",
+                    help="current-source topology: CBAM x 14 + SelfAttention (SURVEY 8 row f1; not the BASELINE config)")
     ap.add_argument("--plans", type=int, default=2, help="independent plans / streams alternating in the device-resident leg")
     ap.add_argument("--depth", type=int, default=4, help="batches in flight in the end-to-end leg (Detector.pipeline_depth)")
     ap.add_argument("--breakdown", default="", help="write the per-op eager timing table to this JSON file")
@@ -166,8 +168,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     C_, d, m = synth.SCALES[args.scale]
-    model = BaseModel(80, C_, d, m).eval()
-    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    model = BaseModel(80, C_, d, m, attention=args.attention).eval()
+    sd_np = synth.make_state_dict(80, C_, d, m, seed=0)
+    if args.attention:
+        sd_np.update(synth.make_attention_state_dict(80, C_, d, m, seed=0))
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()})
     det = Detector(model, (args.size, args.size), confidence=CONF, nms_iou=IOU, letterbox_image=True, pipeline_depth=args.depth)
     B = args.batch
     # rank-distinct synthetic uint8 batches (seed 3 + 17*rank + j), two pinned host copies for the e2e leg
@@ -289,6 +294,10 @@ def main():
                     w, bb, out = payload
                     check(eng.L.tod_stem_conv_nhwc_u8(x_u8.data_ptr(), w.data_ptr(), bb.data_ptr(), out.ptr, B, args.size,
                                                       args.size, C_, out.pitch, st), name)
+                elif kind == "cbam":
+                    check(eng.L.tod_cbam_nhwc_bf16(C.byref(payload), st), name)
+                elif kind == "attn":
+                    eng._run_attention(payload, st)
                 else:
                     buf, c_ = payload
                     check(eng.L.tod_sppf_pool_nhwc_bf16(buf.ptr, B, buf.h, buf.w, c_, buf.pitch, st), name)
@@ -348,7 +357,8 @@ def main():
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"scale {args.scale} detector (BaseModel(80,{C_},{d},{m})), batch {B} per GPU, {args.size}x{args.size}, "
-                                       f"nc 80, conf {CONF} iou {IOU}, random-init weights, uint8 NHWC images (/255 fused into the stem)",
+                                       f"nc 80, conf {CONF} iou {IOU}, random-init weights, uint8 NHWC images (/255 fused into the stem)"
+                                       + (", CURRENT-SOURCE topology (CBAM x 14 + SelfAttention)" if args.attention else ""),
                            "timing": f"CUDA events around K graph replays, {NP} independent plans alternating on {NP} streams (batch i's NMS tail "
                                      "overlaps batch i+1's first layers); activations per pass (~2.5 GB) exceed L2 (126 MB)",
                            "single_pass_latency_ms": pass_latency_ms},
@@ -361,6 +371,8 @@ def main():
                 "clocks": sampler.result(), "roofline": roof, "cpu_baseline": cpu,
                 "breakdown_ms": {"conv": conv_ms, "stem": sum(r["ms"] for r in table if r["kind"] == "stem"),
                                  "pool": sum(r["ms"] for r in table if r["kind"] == "pool"),
+                                 "cbam": sum(r["ms"] for r in table if r["kind"] == "cbam"),
+                                 "attn": sum(r["ms"] for r in table if r["kind"] == "attn"),
                                  "decode": sum(r["ms"] for r in table if r["kind"] == "decode"),
                                  "nms": sum(r["ms"] for r in table if r["kind"] == "nms")},
                 "conv_tflops_whole_pass": eng.conv_flops / 1e12 / (dev_ms / args.steps / 1e3)}
