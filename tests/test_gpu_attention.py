@@ -66,7 +66,8 @@ def _sa_bf16_emulation(sd, x):
     return out + (g * sd["value.bias"]).view(1, -1, 1, 1) + xb
 
 
-def test_self_attention_matches_reference_fixture_and_emulation():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+def test_self_attention_matches_reference_fixture_and_emulation(fused):
     """SelfAttention (unfused tcgen05 GEMMs + row softmax) against the fixture written from the reference module (gamma
     != 0): bf16 q / k move the logits by ~|s| * 2^-8, so the stated tolerance against fp32 is 6e-2 * |ref| + 6e-2; against
     the emulation with the same rounding points it is 2e-2."""
@@ -76,6 +77,7 @@ def test_self_attention_matches_reference_fixture_and_emulation():
         keys = ("query.weight", "query.bias", "key.weight", "key.bias", "value.weight", "value.bias", "gamma")
         sd = {k: torch.from_numpy(g[f"sa{i}_{k}"]) for k in keys}
         m = SelfAttention(int(c))
+        m.fused = fused
         m.load_state_dict(sd)
         x = torch.from_numpy(g[f"sa{i}_x"])
         y = m(x.cuda()).cpu()
@@ -102,13 +104,15 @@ def test_softmax_rows_against_torch():
         assert abs(float(o[:, :cols].float().sum(1).mean()) - 1.0) < 5e-3
 
 
-def test_self_attention_at_network_size():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+def test_self_attention_at_network_size(fused):
     """The backbone's instance at scale s, 640x640 (model/backbone.py:33): C = 128 on the 80x80 map, N = 6400 tokens, one
     image; against the emulation with the same rounding points (f32 scores are 164 MB, bf16 weights 82 MB per image)."""
     from transparent_object_detection_b200.attention import SelfAttention
     g = torch.Generator().manual_seed(8)
     c, h, w = 128, 80, 80
     m = SelfAttention(c)
+    m.fused = fused
     sd = {"query.weight": torch.randn((16, c, 1, 1), generator=g) * 0.08, "query.bias": torch.randn((16,), generator=g) * 0.1,
           "key.weight": torch.randn((16, c, 1, 1), generator=g) * 0.08, "key.bias": torch.randn((16,), generator=g) * 0.1,
           "value.weight": torch.randn((c, c, 1, 1), generator=g) * 0.1, "value.bias": torch.randn((c,), generator=g) * 0.1,
@@ -125,7 +129,8 @@ def test_self_attention_at_network_size():
     emu = _sa_bf16_emulation(sd, x)
     err = (y.cpu() - emu).abs()
     assert float((err > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, float(err.max())
-    print(f"SelfAttention 1 x 128 x 80 x 80 (N = 6400), layout conversions included: {e0.elapsed_time(e1):.2f} ms")
+    print(f"SelfAttention 1 x 128 x 80 x 80 (N = 6400), {'fused' if fused else 'unfused'}, layout conversions included: "
+          f"{e0.elapsed_time(e1):.2f} ms")
 
 
 def test_current_source_network_matches_reference_fixture():

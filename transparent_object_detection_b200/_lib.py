@@ -18,7 +18,7 @@ SYMBOLS = (
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
     "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
     "tod_conv2d_tail1x1_box_decode", "tod_cbam_workspace_floats", "tod_cbam_nhwc_bf16",
-    "tod_softmax_rows_f32_bf16",
+    "tod_softmax_rows_f32_bf16", "tod_attention_fused",
 )
 
 
@@ -70,6 +70,12 @@ class CbamDesc(C.Structure):
                 ("d_conv", C.c_void_p), ("d_work", C.c_void_p),
                 ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("hidden", C.c_int32),
                 ("ksize", C.c_int32), ("x_pitch", C.c_int32), ("out_pitch", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class AttentionDesc(C.Structure):
+    _fields_ = [("d_q", C.c_void_p), ("d_k", C.c_void_p), ("d_vt", C.c_void_p), ("d_bias", C.c_void_p), ("d_x", C.c_void_p),
+                ("d_out", C.c_void_p), ("batch", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("d16", C.c_int32),
+                ("x_pitch", C.c_int32), ("out_pitch", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class ConvTailDesc(C.Structure):
@@ -127,6 +133,7 @@ def lib() -> C.CDLL:
     L.tod_cbam_workspace_floats.restype = C.c_int64
     L.tod_cbam_nhwc_bf16.argtypes = [C.POINTER(CbamDesc), C.c_void_p]
     L.tod_softmax_rows_f32_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
+    L.tod_attention_fused.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
     L.tod_correct_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)  # fail loudly if the binary is stale

@@ -67,6 +67,52 @@ def _gemm(L, st, x_ptr, h, w, cin, x_pitch, w_ptr, cout, out_ptr, out_pitch, out
     check(L.tod_conv2d_nhwc_bf16(C.byref(d), st), what)
 
 
+def self_attention_fused_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: float) -> torch.Tensor:
+    """The same block with tod_attention_fused (csrc/attention_tcgen05.cu): q / k projections over the whole batch, V^T per
+    image, then ONE kernel that keeps the scores and the attention weights on chip."""
+    from ._lib import AttentionDesc
+    from .engine import pack_conv_weight
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()):
+        raise ValueError("x must be a contiguous bf16 CUDA tensor (B, H, W, C)")
+    B, H, W, Cc = x.shape
+    N = H * W
+    if N % 16 or Cc % 32 or Cc > 256:
+        raise ValueError(f"fused SelfAttention needs H * W % 16 == 0 and C % 32 == 0, C <= 256 (got {H}x{W}, C = {Cc})")
+    dev, L = x.device, lib()
+    d = wq.shape[0]
+    d16 = 16 if d <= 16 else (32 if d <= 32 else 64)
+    if d > 64:
+        raise ValueError("fused SelfAttention supports q/k widths up to 64")
+
+    def padded(wt, bs):
+        wp, bp = torch.zeros((d16, Cc, 1, 1)), torch.zeros((d16,))
+        wp[:d], bp[:d] = wt.detach().float().cpu().reshape(d, Cc, 1, 1), bs.detach().float().cpu()
+        return pack_conv_weight(wp).to(dev), bp.to(dev)
+
+    wq_p, bq_p = padded(wq, bq)
+    wk_p, bk_p = padded(wk, bk)
+    wv_g = (float(gamma) * wv.detach().float().cpu().reshape(Cc, Cc)).to(torch.bfloat16).to(dev).contiguous()
+    bv_g = (float(gamma) * bv.detach().float().cpu()).to(dev).contiguous()
+    q = torch.empty((B, N, d16), dtype=torch.bfloat16, device=dev)
+    k = torch.empty_like(q)
+    vT = torch.empty((B, Cc, N), dtype=torch.bfloat16, device=dev)
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _gemm(L, st, x.data_ptr(), B * H, W, Cc, Cc, wq_p.data_ptr(), d16, q.data_ptr(), d16, bias_ptr=bq_p.data_ptr(), what="query")
+        _gemm(L, st, x.data_ptr(), B * H, W, Cc, Cc, wk_p.data_ptr(), d16, k.data_ptr(), d16, bias_ptr=bk_p.data_ptr(), what="key")
+        for i in range(B):
+            _gemm(L, st, wv_g.data_ptr(), 1, Cc, Cc, Cc, x.data_ptr() + i * N * Cc * 2, N, vT.data_ptr() + i * Cc * N * 2, N,
+                  what="value^T")
+        a = AttentionDesc()
+        a.d_q, a.d_k, a.d_vt, a.d_bias = q.data_ptr(), k.data_ptr(), vT.data_ptr(), bv_g.data_ptr()
+        a.d_x, a.d_out = x.data_ptr(), out.data_ptr()
+        a.batch, a.n, a.c, a.d16, a.x_pitch, a.out_pitch = B, N, Cc, d16, Cc, Cc
+        check(L.tod_attention_fused(C.byref(a), st), "tod_attention_fused")
+        torch.cuda.current_stream(dev).synchronize()
+    return out
+
+
 def self_attention_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: float) -> torch.Tensor:
     """reference SelfAttention.forward (model/blocks.py:236-254) on a dense NHWC bf16 CUDA tensor (B, H, W, C), H * W % 16
     == 0.  UNFUSED baseline: per image the N x N scores are materialised (f32), soft-maxed into bf16 weights and applied
@@ -132,9 +178,12 @@ class SelfAttention(nn.Module):
         self.value = nn.Conv2d(channels, channels, kernel_size=1)
         self.gamma = nn.Parameter(torch.zeros(1))
 
+    fused = True      # tod_attention_fused when the shape allows it (C % 32 == 0, C <= 256); else the unfused GEMM chain
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
         xn = x.to(dev).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-        y = self_attention_nhwc(xn, self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight,
+        fn = self_attention_fused_nhwc if (self.fused and xn.shape[3] % 32 == 0 and xn.shape[3] <= 256) else self_attention_nhwc
+        y = fn(xn, self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight,
                                 self.value.bias, float(self.gamma.detach()))
         return y.permute(0, 3, 1, 2).to(x.dtype).to(x.device)

@@ -23,6 +23,7 @@ SOURCES = {
     "letterbox.cu": [],
     "cbam.cu": [],
     "softmax.cu": [],
+    "attention_tcgen05.cu": [],
     "head_decode.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],
 }

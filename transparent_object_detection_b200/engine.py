@@ -176,6 +176,9 @@ class DetectorEngine:
         wq, wk = _t(sd, prefix + ".query.weight").float(), _t(sd, prefix + ".key.weight").float()
         dq = wq.shape[0]
         d16 = (dq + 15) // 16 * 16
+        fused = Cc % 32 == 0 and Cc <= 256 and dq <= 64 and os.environ.get("TOD_ATTN_FUSED", "1") != "0"
+        if fused:
+            d16 = 16 if dq <= 16 else (32 if dq <= 32 else 64)
         gamma = float(_t(sd, prefix + ".gamma").reshape(-1)[0])
 
         def padded(wt, bs):
@@ -183,13 +186,17 @@ class DetectorEngine:
             wp[:dq], bp[:dq] = wt.reshape(dq, Cc, 1, 1), bs.float()
             return self._dev(pack_conv_weight(wp)), self._dev(bp)
 
-        plan = dict(v=v, N=N, C=Cc, d16=d16)
+        plan = dict(v=v, N=N, C=Cc, d16=d16, fused=fused)
         plan["wq"], plan["bq"] = padded(wq, _t(sd, prefix + ".query.bias"))
         plan["wk"], plan["bk"] = padded(wk, _t(sd, prefix + ".key.bias"))
         plan["wv"] = self._dev((gamma * _t(sd, prefix + ".value.weight").float().reshape(Cc, Cc)).to(torch.bfloat16))
         plan["bv"] = self._dev(gamma * _t(sd, prefix + ".value.bias").float())
-        for name, shape, dt in (("q", (self.batch, N, d16), torch.bfloat16), ("k", (self.batch, N, d16), torch.bfloat16),
-                                ("S", (N, N), torch.float32), ("P", (N, N), torch.bfloat16), ("vT", (Cc, N), torch.bfloat16)):
+        temps = [("q", (self.batch, N, d16), torch.bfloat16), ("k", (self.batch, N, d16), torch.bfloat16)]
+        if fused:      # tod_attention_fused: the scores never leave the SM
+            temps += [("vT", (self.batch, Cc, N), torch.bfloat16)]
+        else:
+            temps += [("S", (N, N), torch.float32), ("P", (N, N), torch.bfloat16), ("vT", (Cc, N), torch.bfloat16)]
+        for name, shape, dt in temps:
             plan[name] = torch.zeros(shape, dtype=dt, device=self.device)
             self._keep.append(plan[name])
         self.ops.append(("attn", prefix, plan))
@@ -198,6 +205,22 @@ class DetectorEngine:
     def _run_attention(self, plan: dict, st: int) -> None:
         from .attention import _gemm
         L, v, N, Cc, d16 = self.L, plan["v"], plan["N"], plan["C"], plan["d16"]
+        if plan["fused"]:
+            from ._lib import AttentionDesc
+            B = self.batch
+            _gemm(L, st, v.ptr, B * v.h, v.w, Cc, Cc, plan["wq"].data_ptr(), d16, plan["q"].data_ptr(), d16,
+                  bias_ptr=plan["bq"].data_ptr(), what="query")
+            _gemm(L, st, v.ptr, B * v.h, v.w, Cc, Cc, plan["wk"].data_ptr(), d16, plan["k"].data_ptr(), d16,
+                  bias_ptr=plan["bk"].data_ptr(), what="key")
+            for i in range(B):
+                _gemm(L, st, plan["wv"].data_ptr(), 1, Cc, Cc, Cc, v.ptr + i * N * Cc * 2, N,
+                      plan["vT"].data_ptr() + i * Cc * N * 2, N, what="value^T")
+            a = AttentionDesc()
+            a.d_q, a.d_k, a.d_vt, a.d_bias = plan["q"].data_ptr(), plan["k"].data_ptr(), plan["vT"].data_ptr(), plan["bv"].data_ptr()
+            a.d_x, a.d_out = v.ptr, v.ptr
+            a.batch, a.n, a.c, a.d16, a.x_pitch, a.out_pitch = B, N, Cc, d16, Cc, Cc
+            check(L.tod_attention_fused(C.byref(a), st), "tod_attention_fused")
+            return
         for i in range(self.batch):
             xi = v.ptr + i * N * Cc * 2
             qi, ki = plan["q"].data_ptr() + i * N * d16 * 2, plan["k"].data_ptr() + i * N * d16 * 2
@@ -506,7 +529,8 @@ class DetectorEngine:
     # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
     @property
     def launches_per_pass(self) -> int:
-        extra = sum(3 if k == "cbam" else (6 * self.batch - 1 if k == "attn" else 0) for k, _, _ in self.ops)
+        extra = sum(4 if k == "cbam" else (((self.batch + 2) if p["fused"] else 6 * self.batch - 1) if k == "attn" else 0)
+                    for k, _, p in self.ops)
         return (len(self.ops) + extra - len(self.tail_skip) - (len(self.tail_box_skip) if self.fuse_head_decode else 0)
                 + (0 if self.fuse_head_decode else 1) + 3)
 
