@@ -325,6 +325,10 @@ typedef struct tod_attention_desc {
   int32_t reserved[4];
 } tod_attention_desc;
 int tod_attention_fused(const tod_attention_desc* desc, void* stream);
+/* [batch, rows, in_pitch] bf16 -> [batch, cols, out_pitch] bf16 transposed per image (the value projection [B, N, C] of the
+ * batched 1x1 conv -> V^T [B, C, N] for tod_attention_fused; replaces the .view / .permute of model/blocks.py:241,250). */
+int tod_transpose_bf16(const void* d_in, void* d_out, int32_t batch, int32_t rows, int32_t cols, int64_t in_pitch,
+                       int64_t out_pitch, void* stream);
 
 /* Debug/verification helper used by tests only: direct (non-tensor-core) evaluation of the same conv
  * descriptor on CUDA cores, fp32 accumulate.  Never called by the product path. */

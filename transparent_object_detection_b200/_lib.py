@@ -18,7 +18,7 @@ SYMBOLS = (
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
     "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
     "tod_conv2d_tail1x1_box_decode", "tod_cbam_workspace_floats", "tod_cbam_nhwc_bf16",
-    "tod_softmax_rows_f32_bf16", "tod_attention_fused",
+    "tod_softmax_rows_f32_bf16", "tod_attention_fused", "tod_transpose_bf16",
 )
 
 
@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
     L.tod_cbam_workspace_floats.restype = C.c_int64
     L.tod_cbam_nhwc_bf16.argtypes = [C.POINTER(CbamDesc), C.c_void_p]
     L.tod_softmax_rows_f32_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
+    L.tod_transpose_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
     L.tod_attention_fused.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
     L.tod_correct_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:

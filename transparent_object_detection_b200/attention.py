@@ -101,9 +101,10 @@ def self_attention_fused_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: fl
         st = torch.cuda.current_stream(dev).cuda_stream
         _gemm(L, st, x.data_ptr(), B * H, W, Cc, Cc, wq_p.data_ptr(), d16, q.data_ptr(), d16, bias_ptr=bq_p.data_ptr(), what="query")
         _gemm(L, st, x.data_ptr(), B * H, W, Cc, Cc, wk_p.data_ptr(), d16, k.data_ptr(), d16, bias_ptr=bk_p.data_ptr(), what="key")
-        for i in range(B):
-            _gemm(L, st, wv_g.data_ptr(), 1, Cc, Cc, Cc, x.data_ptr() + i * N * Cc * 2, N, vT.data_ptr() + i * Cc * N * 2, N,
-                  what="value^T")
+        wv_p = pack_conv_weight((float(gamma) * wv.detach().float().cpu()).reshape(Cc, Cc, 1, 1)).to(dev)
+        vn = torch.empty((B, N, Cc), dtype=torch.bfloat16, device=dev)
+        _gemm(L, st, x.data_ptr(), B * H, W, Cc, Cc, wv_p.data_ptr(), Cc, vn.data_ptr(), Cc, what="value")
+        check(L.tod_transpose_bf16(vn.data_ptr(), vT.data_ptr(), B, N, Cc, Cc, N, st), "tod_transpose_bf16")
         a = AttentionDesc()
         a.d_q, a.d_k, a.d_vt, a.d_bias = q.data_ptr(), k.data_ptr(), vT.data_ptr(), bv_g.data_ptr()
         a.d_x, a.d_out = x.data_ptr(), out.data_ptr()

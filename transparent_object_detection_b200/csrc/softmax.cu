@@ -49,9 +49,51 @@ __global__ void __launch_bounds__(kSoftmaxThreads) softmax_rows_kernel(const flo
   }
 }
 
+// [batch][rows][cols] bf16 -> [batch][cols][rows] bf16 through a 64 x 64 shared-memory tile: the value projection of
+// SelfAttention comes out of the batched 1x1 conv as [B, N, C] and the attention kernel wants V^T [B, C, N] (K-major for
+// P . V^T).  One launch instead of one small GEMM per image.
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                            int rows, int cols, long long in_pitch, long long out_pitch) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const __nv_bfloat16* src = in + static_cast<long long>(blockIdx.z) * rows * in_pitch;
+  __nv_bfloat16* dst = out + static_cast<long long>(blockIdx.z) * cols * out_pitch;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {          // 64 rows x 32 bf16 pairs
+    const int r = i >> 5, cp = (i & 31) * 2;
+    if (r0 + r < rows && c0 + cp < cols) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + (r0 + r) * in_pitch + c0 + cp);
+      tile[r][cp] = v.x;
+      tile[r][cp + 1] = v.y;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {          // 64 output rows (= input columns) x 32 pairs of input rows
+    const int c = i >> 5, rp = (i & 31) * 2;
+    if (c0 + c < cols && r0 + rp < rows) {
+      __nv_bfloat162 v;
+      v.x = tile[rp][c];
+      v.y = tile[rp + 1][c];
+      *reinterpret_cast<__nv_bfloat162*>(dst + (c0 + c) * out_pitch + r0 + rp) = v;
+    }
+  }
+}
+
 }  // namespace tod
 
 using namespace tod;
+
+extern "C" int tod_transpose_bf16(const void* d_in, void* d_out, int32_t batch, int32_t rows, int32_t cols, int64_t in_pitch,
+                                  int64_t out_pitch, void* stream) {
+  TOD_CHECK_ARG(d_in != nullptr && d_out != nullptr, "transpose: null pointer");
+  TOD_CHECK_ARG(batch > 0 && batch <= 65535 && rows > 0 && cols > 0 && rows % 2 == 0 && cols % 2 == 0 && in_pitch >= cols &&
+                    out_pitch >= rows && in_pitch % 2 == 0 && out_pitch % 2 == 0,
+                "transpose: batch %d rows %d cols %d (even sizes and pitches)", batch, rows, cols);
+  TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d_in) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0, "transpose: alignment");
+  transpose_bf16_kernel<<<dim3((rows + 63) / 64, (cols + 63) / 64, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_in), reinterpret_cast<__nv_bfloat16*>(d_out), rows, cols, in_pitch, out_pitch);
+  TOD_CHECK_LAUNCH("transpose_bf16_kernel launch");
+  return TOD_OK;
+}
 
 extern "C" int tod_softmax_rows_f32_bf16(const float* d_in, void* d_out, int32_t rows, int32_t cols, int64_t in_pitch,
                                          int64_t out_pitch, void* stream) {

@@ -192,8 +192,9 @@ class DetectorEngine:
         plan["wv"] = self._dev((gamma * _t(sd, prefix + ".value.weight").float().reshape(Cc, Cc)).to(torch.bfloat16))
         plan["bv"] = self._dev(gamma * _t(sd, prefix + ".value.bias").float())
         temps = [("q", (self.batch, N, d16), torch.bfloat16), ("k", (self.batch, N, d16), torch.bfloat16)]
-        if fused:      # tod_attention_fused: the scores never leave the SM
-            temps += [("vT", (self.batch, Cc, N), torch.bfloat16)]
+        if fused:      # tod_attention_fused: the scores never leave the SM; v = x (gamma Wv)^T batched, then transposed
+            temps += [("vT", (self.batch, Cc, N), torch.bfloat16), ("vn", (self.batch, N, Cc), torch.bfloat16)]
+            plan["wvp"] = self._dev(pack_conv_weight((gamma * _t(sd, prefix + ".value.weight").float()).reshape(Cc, Cc, 1, 1)))
         else:
             temps += [("S", (N, N), torch.float32), ("P", (N, N), torch.bfloat16), ("vT", (Cc, N), torch.bfloat16)]
         for name, shape, dt in temps:
@@ -212,9 +213,8 @@ class DetectorEngine:
                   bias_ptr=plan["bq"].data_ptr(), what="query")
             _gemm(L, st, v.ptr, B * v.h, v.w, Cc, Cc, plan["wk"].data_ptr(), d16, plan["k"].data_ptr(), d16,
                   bias_ptr=plan["bk"].data_ptr(), what="key")
-            for i in range(B):
-                _gemm(L, st, plan["wv"].data_ptr(), 1, Cc, Cc, Cc, v.ptr + i * N * Cc * 2, N,
-                      plan["vT"].data_ptr() + i * Cc * N * 2, N, what="value^T")
+            _gemm(L, st, v.ptr, B * v.h, v.w, Cc, Cc, plan["wvp"].data_ptr(), Cc, plan["vn"].data_ptr(), Cc, what="value")
+            check(L.tod_transpose_bf16(plan["vn"].data_ptr(), plan["vT"].data_ptr(), B, N, Cc, Cc, N, st), "tod_transpose_bf16")
             a = AttentionDesc()
             a.d_q, a.d_k, a.d_vt, a.d_bias = plan["q"].data_ptr(), plan["k"].data_ptr(), plan["vT"].data_ptr(), plan["bv"].data_ptr()
             a.d_x, a.d_out = v.ptr, v.ptr
@@ -529,7 +529,7 @@ class DetectorEngine:
     # number of kernels one full pass enqueues (forward ops + decode + 3 NMS kernels)
     @property
     def launches_per_pass(self) -> int:
-        extra = sum(4 if k == "cbam" else (((self.batch + 2) if p["fused"] else 6 * self.batch - 1) if k == "attn" else 0)
+        extra = sum(4 if k == "cbam" else ((4 if p["fused"] else 6 * self.batch - 1) if k == "attn" else 0)
                     for k, _, p in self.ops)
         return (len(self.ops) + extra - len(self.tail_skip) - (len(self.tail_box_skip) if self.fuse_head_decode else 0)
                 + (0 if self.fuse_head_decode else 1) + 3)
