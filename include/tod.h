@@ -309,7 +309,9 @@ int tod_softmax_rows_f32_bf16(const float* d_in, void* d_out, int32_t rows, int3
  * Fused self-attention on tcgen05 / TMEM: the N x N scores never leave the SM.
  * Replaces: torch.bmm(query, key) -> softmax -> torch.bmm(value, attention^T) -> gamma * out + x
  *           SelfAttention.forward  model/blocks.py:243-253 (the three 1x1 projections :239-241 are tod_conv2d_nhwc_bf16 calls).
- *   d_q, d_k  bf16 [batch, n, d16]   query / key projections (+ bias), channels zero-padded to d16 in {16, 32, 64}
+ *   d_q, d_k  bf16 [batch, n, d16]   query / key projections (+ bias), channels zero-padded to d16 in {16, 32, 64};
+ *                                    the QUERY projection (weights and bias) is pre-multiplied by log2(e): the kernel
+ *                                    evaluates the softmax with base-2 exponentials
  *   d_vt      bf16 [batch, c, n]     (gamma * Wv) . x^T per image (value projection without bias, transposed: K-major for P . V)
  *   d_bias    f32 [c] = gamma * b_v  (softmax rows sum to one, so the value bias moves out of the sum) or NULL
  *   d_x       bf16 [batch, n, x_pitch] residual; d_out bf16 [batch, n, out_pitch] (may alias d_x); n % 16 == 0, c % 32 == 0, c <= 256

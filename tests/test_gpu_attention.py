@@ -50,14 +50,17 @@ def test_cbam_in_place_channel_window_and_large_plane():
     assert float((err > 1e-2 * ref.abs() + 1e-2).float().mean()) == 0.0
 
 
-def _sa_bf16_emulation(sd, x):
+def _sa_bf16_emulation(sd, x, fused=False):
     """The oracle's SelfAttention with the build's rounding points: bf16 input, q / k / gamma-scaled v rounded to bf16,
-    f32 scores, bf16 attention weights, f32 accumulation."""
+    f32 scores, bf16 attention weights, f32 accumulation.  fused: the query projection carries log2(e) before it is
+    rounded to bf16 (tod_attention_fused evaluates the softmax with base-2 exponentials)."""
+    import math
     import torch.nn.functional as F
     bf = lambda t: t.to(torch.bfloat16).float()
     b, c, h, w = x.shape
     xb = bf(x)
-    q = bf(F.conv2d(xb, bf(sd["query.weight"]), sd["query.bias"])).view(b, -1, h * w).permute(0, 2, 1)
+    qs = math.log2(math.e) if fused else 1.0
+    q = bf(F.conv2d(xb, bf(qs * sd["query.weight"]), qs * sd["query.bias"])).view(b, -1, h * w).permute(0, 2, 1) / qs
     k = bf(F.conv2d(xb, bf(sd["key.weight"]), sd["key.bias"])).view(b, -1, h * w)
     g = float(sd["gamma"])
     v = bf(F.conv2d(xb, bf(g * sd["value.weight"]), None)).view(b, -1, h * w)
@@ -83,7 +86,7 @@ def test_self_attention_matches_reference_fixture_and_emulation(fused):
         y = m(x.cuda()).cpu()
         ref = torch.from_numpy(g[f"sa{i}_y"])
         assert float(((y - ref).abs() > 6e-2 * ref.abs() + 6e-2).float().mean()) <= 2e-3, (i, float((y - ref).abs().max()))
-        emu = _sa_bf16_emulation(sd, x)
+        emu = _sa_bf16_emulation(sd, x, fused)
         assert float(((y - emu).abs() > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, (i, float((y - emu).abs().max()))
         assert float((y - x).abs().max()) > 0.1                      # gamma != 0: the attention term is really there
 
@@ -126,7 +129,7 @@ def test_self_attention_at_network_size(fused):
     y = m(xc)
     e1.record()
     torch.cuda.synchronize()
-    emu = _sa_bf16_emulation(sd, x)
+    emu = _sa_bf16_emulation(sd, x, fused)
     err = (y.cpu() - emu).abs()
     assert float((err > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, float(err.max())
     print(f"SelfAttention 1 x 128 x 80 x 80 (N = 6400), {'fused' if fused else 'unfused'}, layout conversions included: "

@@ -10,6 +10,8 @@ import torch.nn as nn
 
 from ._lib import CbamDesc, check, lib
 
+LOG2E = 1.4426950408889634
+
 
 def cbam_nhwc(x: torch.Tensor, fc1: torch.Tensor, fc2: torch.Tensor, conv: torch.Tensor, out: torch.Tensor = None,
               channels: int = None) -> torch.Tensor:
@@ -84,14 +86,13 @@ def self_attention_fused_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: fl
     if d > 64:
         raise ValueError("fused SelfAttention supports q/k widths up to 64")
 
-    def padded(wt, bs):
+    def padded(wt, bs, scale=1.0):
         wp, bp = torch.zeros((d16, Cc, 1, 1)), torch.zeros((d16,))
-        wp[:d], bp[:d] = wt.detach().float().cpu().reshape(d, Cc, 1, 1), bs.detach().float().cpu()
+        wp[:d], bp[:d] = scale * wt.detach().float().cpu().reshape(d, Cc, 1, 1), scale * bs.detach().float().cpu()
         return pack_conv_weight(wp).to(dev), bp.to(dev)
 
-    wq_p, bq_p = padded(wq, bq)
+    wq_p, bq_p = padded(wq, bq, LOG2E)          # base-2 logits: the kernel's softmax is one MUFU.EX2 per score
     wk_p, bk_p = padded(wk, bk)
-    wv_g = (float(gamma) * wv.detach().float().cpu().reshape(Cc, Cc)).to(torch.bfloat16).to(dev).contiguous()
     bv_g = (float(gamma) * bv.detach().float().cpu()).to(dev).contiguous()
     q = torch.empty((B, N, d16), dtype=torch.bfloat16, device=dev)
     k = torch.empty_like(q)

@@ -1,7 +1,8 @@
 // Fused self-attention on tcgen05 / TMEM (sm_100a): the reference's SelfAttention block (model/blocks.py:236-254,
 // instance model/backbone.py:33) without ever materialising the N x N score matrix -- SURVEY.md section 8 row f1.
 //
-//   out[i, :] = sum_j softmax_j(q_i . k_j) * v[j, :]  + bias + x[i, :]          (gamma is folded into v / bias by the host)
+//   out[i, :] = sum_j softmax_j(q_i . k_j) * v[j, :]  + bias + x[i, :]          (gamma is folded into v / bias by the host,
+//                                                                                 log2(e) into q: the scores are base-2 logits)
 //
 // One CTA owns 128 queries of one image and walks the keys in tiles of 128, twice:
 //   pass 1  S = Q K_j^T (one tcgen05.mma, K = d <= 64) -> the softmax threads read S from TMEM and keep the row maximum;
@@ -43,6 +44,12 @@ __device__ __forceinline__ void attn_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ float attn_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_constant__ AttnParams p) {
@@ -158,9 +165,14 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
         uint32_t v[32];
         attn_ld32(tmem_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
+        if (valid == kAttnTile) {            // full tile (all but the last one): no per-element predicates
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (ch * 32 + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -178,12 +190,25 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
         uint32_t v[32], o[16];
         attn_ld32(tmem_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
+        // the host folds log2(e) into the query projection, so the scores are base-2 logits: one MUFU.EX2 per score
+        if (valid == kAttnTile) {
+          float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = ch * 32 + i < valid ? __expf(__uint_as_float(v[i]) - m) : 0.0f;
-          const float e1 = ch * 32 + i + 1 < valid ? __expf(__uint_as_float(v[i + 1]) - m) : 0.0f;
-          l += e0 + e1;
-          o[i >> 1] = pack_bf16x2(e0, e1);
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = attn_ex2(__uint_as_float(v[i]) - m), e1 = attn_ex2(__uint_as_float(v[i + 1]) - m);
+            l0 += e0;
+            l1 += e1;
+            o[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          l += l0 + l1;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = ch * 32 + i < valid ? attn_ex2(__uint_as_float(v[i]) - m) : 0.0f;
+            const float e1 = ch * 32 + i + 1 < valid ? attn_ex2(__uint_as_float(v[i + 1]) - m) : 0.0f;
+            l += e0 + e1;
+            o[i >> 1] = pack_bf16x2(e0, e1);
+          }
         }
         // keys [ch*32, ch*32+32) -> panel ch/2, 16-byte chunks (ch%2)*4 .. +3 of this row, SWIZZLE_128B
         const uint32_t row = p_base + (ch >> 1) * 16384u + static_cast<uint32_t>(r) * 128u;

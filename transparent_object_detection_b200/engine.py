@@ -181,13 +181,13 @@ class DetectorEngine:
             d16 = 16 if dq <= 16 else (32 if dq <= 32 else 64)
         gamma = float(_t(sd, prefix + ".gamma").reshape(-1)[0])
 
-        def padded(wt, bs):
+        def padded(wt, bs, scale=1.0):
             wp, bp = torch.zeros((d16, Cc, 1, 1)), torch.zeros((d16,))
-            wp[:dq], bp[:dq] = wt.reshape(dq, Cc, 1, 1), bs.float()
+            wp[:dq], bp[:dq] = scale * wt.reshape(dq, Cc, 1, 1), scale * bs.float()
             return self._dev(pack_conv_weight(wp)), self._dev(bp)
 
         plan = dict(v=v, N=N, C=Cc, d16=d16, fused=fused)
-        plan["wq"], plan["bq"] = padded(wq, _t(sd, prefix + ".query.bias"))
+        plan["wq"], plan["bq"] = padded(wq, _t(sd, prefix + ".query.bias"), 1.4426950408889634 if fused else 1.0)   # base-2 logits
         plan["wk"], plan["bk"] = padded(wk, _t(sd, prefix + ".key.bias"))
         plan["wv"] = self._dev((gamma * _t(sd, prefix + ".value.weight").float().reshape(Cc, Cc)).to(torch.bfloat16))
         plan["bv"] = self._dev(gamma * _t(sd, prefix + ".value.bias").float())
