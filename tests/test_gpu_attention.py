@@ -173,3 +173,28 @@ def test_current_source_network_matches_reference_fixture():
     assert any(r is not None for r in want_rows)
     for a, b in zip(got_rows, want_rows):
         assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))
+
+
+@pytest.mark.parametrize("c,h,w", [(192, 8, 12), (256, 12, 12), (64, 16, 16), (384, 4, 8)])
+def test_self_attention_other_widths_against_oracle(c, h, w):
+    """The instance's width at the other scales: 4C = 64 (n), 192 (m: q/k width 24 -> 32, two K steps, 64-byte swizzle),
+    256 (l), 384 (x: above the fused kernel's 256 channels -> the unfused GEMM chain), against the oracle on the
+    bf16-rounded input and the emulation with the build's rounding points."""
+    from oracle import detector_oracle as O
+    from transparent_object_detection_b200.attention import SelfAttention
+    g = torch.Generator().manual_seed(c)
+    d = c // 8
+    sd = {"query.weight": torch.randn((d, c, 1, 1), generator=g) * (0.7 / c ** 0.5), "query.bias": torch.randn((d,), generator=g) * 0.1,
+          "key.weight": torch.randn((d, c, 1, 1), generator=g) * (0.7 / c ** 0.5), "key.bias": torch.randn((d,), generator=g) * 0.1,
+          "value.weight": torch.randn((c, c, 1, 1), generator=g) * (1.0 / c ** 0.5), "value.bias": torch.randn((c,), generator=g) * 0.1,
+          "gamma": torch.tensor([0.8])}
+    m = SelfAttention(c)
+    m.load_state_dict(sd)
+    x = torch.randn((2, c, h, w), generator=g)
+    y = m(x.cuda()).cpu()
+    fused = c % 32 == 0 and c <= 256
+    emu = _sa_bf16_emulation(sd, x, fused)
+    assert float(((y - emu).abs() > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, float((y - emu).abs().max())
+    with torch.no_grad():
+        ref = O.self_attention({"m." + k: v for k, v in sd.items()}, "m", x.to(torch.bfloat16).float())
+    assert float(((y - ref).abs() > 6e-2 * ref.abs() + 6e-2).float().mean()) <= 2e-3, float((y - ref).abs().max())
