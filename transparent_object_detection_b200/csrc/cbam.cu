@@ -14,7 +14,7 @@
 namespace tod {
 
 constexpr int kCbamThreads = 256;
-constexpr int kCbamChunkPx = 2048;   // pixels per pooling block
+constexpr int kCbamChunkPx = 512;    // pixels per pooling block (2048 left a 6400-pixel map with 4 x batch blocks: under-filled)
 
 struct CbamParams {
   const __nv_bfloat16* x;
