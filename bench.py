@@ -85,6 +85,36 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Best effort: run this rank (and first-touch its pinned upload buffers) on the NUMA node its GPU hangs off.  With 8
+    ranks each re-reading its host batches at ~30 GB/s, uploads that cross the socket interconnect are what bounds the
+    end-to-end number.  Returns the node or None."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            import pynvml as nv
+            nv.nvmlInit()
+            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_oracle_rate(scale: str, size: int, images: int, min_seconds: float, max_runs: int):
     """images/s of the CPU oracle (forward fp32 + decode_box + NMS) on all host cores."""
     from oracle import detector_oracle as O, synth
@@ -164,6 +194,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -363,7 +394,8 @@ def main():
                                      "overlaps batch i+1's first layers); activations per pass (~2.5 GB) exceed L2 (126 MB)",
                            "single_pass_latency_ms": pass_latency_ms},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(hosts[0].numel()), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_ms / args.steps, "api": f"Detector.submit/collect, {det.pipeline_depth} batches in flight, pinned uint8 host batch",
+                        "ms_per_step": e2e_ms / args.steps, "api": f"Detector.submit/collect, {det.pipeline_depth} batches in flight, pinned uint8 host batch"
+                               + (f" (rank bound to its GPU's NUMA node: {numa_node})" if numa_node is not None else ""),
                         "f32_input": {"value": B * world / (e2e_f32_ms / 1e3), "ms_per_step": e2e_f32_ms,
                                       "h2d_bytes_per_step": int(hosts_f32.numel() * 4),
                                       "api": "Detector.detect (synchronous) on the reference's float32 (B,3,H,W) tensor"}},
