@@ -32,7 +32,7 @@ def fused():
     a.d_q, a.d_k, a.d_vt, a.d_bias, a.d_x, a.d_out = q.data_ptr(), k.data_ptr(), vT.data_ptr(), bv.data_ptr(), x.data_ptr(), out.data_ptr()
     a.batch, a.n, a.c, a.d16, a.x_pitch, a.out_pitch = B, N, Cc, d16, Cc, Cc
     check(L.tod_attention_fused(C.byref(a), st), "fused")
-for name, fn in (("q + k projections", qk), ("V^T per image", vt), ("fused attention kernel", fused)):
+for name, fn in (("q + k projections", qk), ("V^T, one GEMM per image (the path before the batched projection + transpose)", vt), ("fused attention kernel", fused)):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); fn(); fn(); e1.record(); torch.cuda.synchronize()

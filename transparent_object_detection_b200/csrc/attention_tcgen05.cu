@@ -30,7 +30,8 @@ struct __align__(64) AttnParams {
   int n, c, d16, x_pitch, out_pitch, tiles;
   uint32_t qk_bytes, v_panel_bytes;      // one Q / K tile; one 64-key panel of V^T
   uint32_t off_k, off_v, off_p;
-  uint32_t hi_qk, hi_p, hi_v, idesc_s, idesc_o, tmem_cols;
+  uint32_t hi_qk, hi_p, hi_v, idesc_s, idesc_s2, idesc_o, tmem_cols;
+  int tiles2;   // pass 1 walks the keys in tiles of 256 (the O columns of TMEM are free until pass 2) when c >= 128
   int ksteps;
 };
 
@@ -93,13 +94,24 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
     if (elect_one()) {
       mbar_arrive_expect_tx(&q_full, p.qk_bytes);
       tma_load_3d(&p.tm_q, &q_full, smem_base, 0, q0, img);
-      uint32_t kc = 0, vc = 0;
-      for (int pass = 0; pass < 2; ++pass)
-        for (int j = 0; j < T; ++j, ++kc) {
-          const uint32_t ks = kc & 1;
-          mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u);
+      uint32_t use[2] = {0, 0}, vc = 0;      // completed uses of each K slot (barrier phases)
+      if (p.tiles2 > 0) {
+        // pass 1 on 256-key tiles: both K slots as one buffer behind slot 0's barriers
+        for (int j = 0; j < p.tiles2; ++j, ++use[0]) {
+          mbar_wait(&k_empty[0], (use[0] & 1) ^ 1u);
+          mbar_arrive_expect_tx(&k_full[0], 2 * p.qk_bytes);
+          tma_load_3d(&p.tm_k, &k_full[0], smem_base + p.off_k, 0, j * 2 * kAttnTile, img);
+          tma_load_3d(&p.tm_k, &k_full[0], smem_base + p.off_k + p.qk_bytes, 0, j * 2 * kAttnTile + kAttnTile, img);
+        }
+        mbar_wait(&k_empty[0], (use[0] & 1) ^ 1u);   // the last 256-key MMA has read slot 1's memory too
+      }
+      for (int pass = (p.tiles2 > 0 ? 1 : 0); pass < 2; ++pass)
+        for (int j = 0; j < T; ++j) {
+          const uint32_t ks = j & 1;
+          mbar_wait(&k_empty[ks], (use[ks] & 1) ^ 1u);
           mbar_arrive_expect_tx(&k_full[ks], p.qk_bytes);
           tma_load_3d(&p.tm_k, &k_full[ks], smem_base + p.off_k + ks * p.qk_bytes, 0, j * kAttnTile, img);
+          ++use[ks];
           if (pass == 1) {
             const uint32_t vs = vc & 1;
             mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u);
@@ -116,11 +128,24 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
     if (elect_one()) {
       mbar_wait(&q_full, 0);
       const uint32_t q_lo = umma_desc_lo(smem_base);
-      uint32_t kc = 0, vc = 0, sc = 0;
-      for (int pass = 0; pass < 2; ++pass)
-        for (int j = 0; j < T; ++j, ++kc, ++sc) {
-          const uint32_t ks = kc & 1;
-          mbar_wait(&k_full[ks], (kc >> 1) & 1);
+      uint32_t use[2] = {0, 0}, vc = 0, sc = 0;
+      if (p.tiles2 > 0) {
+        const uint32_t k_lo = umma_desc_lo(smem_base + p.off_k);
+        for (int j = 0; j < p.tiles2; ++j, ++use[0], ++sc) {
+          mbar_wait(&k_full[0], use[0] & 1);
+          mbar_wait(&s_free, (sc & 1) ^ 1u);
+          tcgen05_fence_after();
+          for (int s = 0; s < p.ksteps; ++s)     // S (256 columns: the S and O regions) = Q . K^T for 256 keys
+            umma_bf16_k1(tmem_s, q_lo + 2 * s, p.hi_qk, k_lo + 2 * s, p.hi_qk, p.idesc_s2, s != 0 ? 1u : 0u);
+          umma_commit(&k_empty[0]);
+          umma_commit(&s_full);
+        }
+      }
+      for (int pass = (p.tiles2 > 0 ? 1 : 0); pass < 2; ++pass)
+        for (int j = 0; j < T; ++j, ++sc) {
+          const uint32_t ks = j & 1;
+          mbar_wait(&k_full[ks], use[ks] & 1);
+          ++use[ks];
           mbar_wait(&s_free, (sc & 1) ^ 1u);       // the softmax threads have drained the previous S
           tcgen05_fence_after();
           const uint32_t k_lo = umma_desc_lo(smem_base + p.off_k + ks * p.qk_bytes);
@@ -155,17 +180,18 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
     const uint32_t p_base = smem_base + p.off_p;
     float m = -INFINITY;
     uint32_t sc = 0;
-    // pass 1: row maximum
-    for (int j = 0; j < T; ++j, ++sc) {
+    // pass 1: row maximum (256 keys per tile when the O columns can hold the second half of S)
+    const int t1 = p.tiles2 > 0 ? p.tiles2 : T, w1 = p.tiles2 > 0 ? 2 * kAttnTile : kAttnTile;
+    for (int j = 0; j < t1; ++j, ++sc) {
       mbar_wait(&s_full, sc & 1);
       tcgen05_fence_after();
-      const int valid = min(kAttnTile, p.n - j * kAttnTile);
+      const int valid = min(w1, p.n - j * w1);
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < w1 / 32; ++ch) {
         uint32_t v[32];
         attn_ld32(tmem_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
-        if (valid == kAttnTile) {            // full tile (all but the last one): no per-element predicates
+        if (valid == w1) {                   // full tile (all but the last one): no per-element predicates
 #pragma unroll
           for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
         } else {
@@ -328,6 +354,8 @@ extern "C" int tod_attention_fused(const tod_attention_desc* d, void* stream) {
   p.hi_p = attn_desc_hi(1024, 128);
   p.hi_v = attn_desc_hi(1024, 128);
   p.idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kAttnTile >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc_s2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) | ((128u >> 4) << 24);
+  p.tiles2 = d->c >= kAttnTile ? (d->n + 2 * kAttnTile - 1) / (2 * kAttnTile) : 0;   // needs 256 TMEM columns: S + (idle) O
   p.idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(d->c >> 3) << 17) | ((128u >> 4) << 24);
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(kAttnTile + d->c)) cols <<= 1;
