@@ -141,35 +141,41 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
           umma_commit(&s_full);
         }
       }
-      for (int pass = (p.tiles2 > 0 ? 1 : 0); pass < 2; ++pass)
-        for (int j = 0; j < T; ++j, ++sc) {
-          const uint32_t ks = j & 1;
-          mbar_wait(&k_full[ks], use[ks] & 1);
-          ++use[ks];
-          mbar_wait(&s_free, (sc & 1) ^ 1u);       // the softmax threads have drained the previous S
-          tcgen05_fence_after();
-          const uint32_t k_lo = umma_desc_lo(smem_base + p.off_k + ks * p.qk_bytes);
-          for (int s = 0; s < p.ksteps; ++s)
-            umma_bf16_k1(tmem_s, q_lo + 2 * s, p.hi_qk, k_lo + 2 * s, p.hi_qk, p.idesc_s, s != 0 ? 1u : 0u);
-          umma_commit(&k_empty[ks]);
-          umma_commit(&s_full);
-          if (pass == 1) {
-            const uint32_t vs = vc & 1;
-            mbar_wait(&p_ready, j & 1);
-            mbar_wait(&v_full[vs], (vc >> 1) & 1);
-            tcgen05_fence_after();
+      auto issue_s = [&](int j) {              // S = Q . K_j^T once the softmax threads have drained the previous S
+        const uint32_t ks = j & 1;
+        mbar_wait(&k_full[ks], use[ks] & 1);
+        ++use[ks];
+        mbar_wait(&s_free, (sc & 1) ^ 1u);
+        ++sc;
+        tcgen05_fence_after();
+        const uint32_t k_lo = umma_desc_lo(smem_base + p.off_k + ks * p.qk_bytes);
+        for (int s = 0; s < p.ksteps; ++s)
+          umma_bf16_k1(tmem_s, q_lo + 2 * s, p.hi_qk, k_lo + 2 * s, p.hi_qk, p.idesc_s, s != 0 ? 1u : 0u);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full);
+      };
+      if (p.tiles2 == 0)
+        for (int j = 0; j < T; ++j) issue_s(j);                       // pass 1 on 128-key tiles (c < 128)
+      // pass 2: the softmax threads release S as soon as they have READ it, so S_{j+1} is issued before P_j V_j^T and its
+      // latency runs under the exponentials of tile j
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        const uint32_t vs = vc & 1;
+        mbar_wait(&p_ready, j & 1);
+        mbar_wait(&v_full[vs], (vc >> 1) & 1);
+        tcgen05_fence_after();
 #pragma unroll 1
-            for (int pn = 0; pn < 2; ++pn) {
-              const uint32_t a_lo = umma_desc_lo(smem_base + p.off_p + pn * 16384u);
-              const uint32_t b_lo = umma_desc_lo(smem_base + p.off_v + (vs * 2 + pn) * p.v_panel_bytes);
-              umma_bf16_k4(tmem_o, a_lo, p.hi_p, b_lo, p.hi_v, p.idesc_o, (j | pn) != 0 ? 1u : 0u);
-            }
-            umma_commit(&v_empty[vs]);
-            umma_commit(&p_free);
-            if (j == T - 1) umma_commit(&o_done);
-            ++vc;
-          }
+        for (int pn = 0; pn < 2; ++pn) {
+          const uint32_t a_lo = umma_desc_lo(smem_base + p.off_p + pn * 16384u);
+          const uint32_t b_lo = umma_desc_lo(smem_base + p.off_v + (vs * 2 + pn) * p.v_panel_bytes);
+          umma_bf16_k4(tmem_o, a_lo, p.hi_p, b_lo, p.hi_v, p.idesc_o, (j | pn) != 0 ? 1u : 0u);
         }
+        umma_commit(&v_empty[vs]);
+        umma_commit(&p_free);
+        if (j == T - 1) umma_commit(&o_done);
+        ++vc;
+      }
     }
     __syncwarp();
   } else {
@@ -211,11 +217,9 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
       tcgen05_fence_after();
       const int valid = min(kAttnTile, p.n - j * kAttnTile);
       mbar_wait(&p_free, (j & 1) ^ 1u);          // the MMAs of the previous tile have finished reading the panels
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32], o[16];
-        attn_ld32(tmem_s + lane_sel + ch * 32, v);
-        tmem_ld_wait();
+      // one chunk's TMEM load is in flight while the previous chunk's exponentials run
+      auto process = [&](int ch, const uint32_t (&v)[32]) {
+        uint32_t o[16];
         // the host folds log2(e) into the query projection, so the scores are base-2 logits: one MUFU.EX2 per score
         if (valid == kAttnTile) {
           float l0 = 0.0f, l1 = 0.0f;
@@ -245,14 +249,28 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
                        "r"(o[4 * c4 + 2]), "r"(o[4 * c4 + 3])
                        : "memory");
         }
+      };
+      {
+        uint32_t va[32], vb[32];
+        attn_ld32(tmem_s + lane_sel, va);
+        tmem_ld_wait();
+        attn_ld32(tmem_s + lane_sel + 32, vb);
+        process(0, va);
+        tmem_ld_wait();
+        attn_ld32(tmem_s + lane_sel + 64, va);
+        process(1, vb);
+        tmem_ld_wait();
+        attn_ld32(tmem_s + lane_sel + 96, vb);
+        process(2, va);
+        tmem_ld_wait();
+        tcgen05_fence_before();                 // S has been read completely: hand it back before the last exponentials
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free);
+        process(3, vb);
       }
       fence_proxy_async_smem();
-      tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_free);
-        mbar_arrive(&p_ready);
-      }
+      if (lane == 0) mbar_arrive(&p_ready);
     }
     // epilogue: out = O / l + bias + x
     mbar_wait(&o_done, 0);
