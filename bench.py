@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
     v = images / (ms / 1e3)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC.replace("640", str(args.size)), "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"scale {args.scale} detector, {args.size}x{args.size}, nc 80, conf {CONF} iou {IOU}; "
@@ -384,7 +384,7 @@ def main():
             v, cores, runs = cpu_oracle_rate(args.scale, args.size, 8, 10.0, 6)
             cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": f"8 images per run x {runs} runs of the CPU oracle (fp32 torch forward + decode + numpy NMS), median"}
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC.replace("640", str(args.size)), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"scale {args.scale} detector (BaseModel(80,{C_},{d},{m})), batch {B} per GPU, {args.size}x{args.size}, "
