@@ -94,3 +94,15 @@ def test_correct_boxes_matches_reference_fixture(golden):
     for lb, key in ((True, "cb_letterbox"), (False, "cb_plain")):
         got = T.DecodeBox.correct_boxes(g["cb_xy"].copy(), g["cb_wh"].copy(), (640, 640), (375, 500), lb)
         np.testing.assert_array_equal(got, g[key])
+
+
+def test_top_boxes_follows_the_reference_selection():
+    """Detector.top_boxes == utils/callbacks.py:163-166 (argsort ascending, reversed, first max_boxes)."""
+    import numpy as np
+    from transparent_object_detection_b200.model import Detector
+    det = Detector.__new__(Detector)
+    det.max_boxes = 3
+    rows = np.array([[0, 0, 1, 1, 0.2, 1], [0, 0, 1, 1, 0.9, 2], [0, 0, 1, 1, 0.5, 0], [0, 0, 1, 1, 0.7, 4], [0, 0, 1, 1, 0.1, 3]], np.float32)
+    got = det.top_boxes(rows)
+    assert got[:, 4].tolist() == [np.float32(0.9), np.float32(0.7), np.float32(0.5)]
+    assert det.top_boxes(None) is None

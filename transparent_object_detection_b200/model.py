@@ -466,6 +466,13 @@ class Detector:
         pending.d2h_bytes = counts.nbytes + int(counts.max() if len(counts) else 0) * counts.shape[0] * 24
         return rows
 
+    def top_boxes(self, rows: Optional[np.ndarray]) -> Optional[np.ndarray]:
+        """The `max_boxes` highest-scoring rows in the reference's order (utils/callbacks.py:163-166:
+        `np.argsort(top_conf)[::-1][:self.max_boxes]` -- the same numpy call, hence the same tie order)."""
+        if rows is None:
+            return None
+        return rows[np.argsort(rows[:, 4])[::-1][:self.max_boxes]]
+
     def detect_image_rows(self, image) -> Optional[np.ndarray]:
         """One PIL image / (H, W, 3) uint8 array -> the reference's (n, 6) rows or None.  The raw pixels go to the GPU as
         they are; the letterbox (utils/utils.py:16-30, bit-exact with Pillow BICUBIC) runs there and /255 is fused into
