@@ -12,14 +12,16 @@
 // Recomputing S is cheap (K = 16 against K = 128 for P V); what it buys is one exponential per score instead of two and no
 // TMEM read-modify-write of O.  Shared memory ~108 KB and 256 TMEM columns at C = 128: two CTAs per SM, so one CTA's
 // softmax (MUFU-bound: 128 exponentials per row per tile) overlaps the other's MMAs without intra-CTA pipelining.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 softmax + epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..9 softmax + epilogue -- two warps
+// per TMEM lane quarter, each taking one half of a tile's keys (= one of the two P panels); with four softmax warps per
+// CTA ncu showed MUFU at 40 % and issue slots at 35 %: latency-bound (profiles/r1_attention_ncu_full_summary.txt).
 #include <mutex>
 
 #include "tma_host.cuh"
 
 namespace tod {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;   // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter: one per half of the keys)
 constexpr int kAttnTile = 128;   // queries per CTA = keys per tile
 
 struct __align__(64) AttnParams {
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_ready, p_free, o_done;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xch[2][kAttnTile];          // row maximum / row sum exchange between the two halves of a row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int q0 = blockIdx.x * kAttnTile, img = blockIdx.y;
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(&s_full, 1);
-    mbar_init(&s_free, 4);     // one arrival per softmax warp
-    mbar_init(&p_ready, 4);
+    mbar_init(&s_free, 8);     // one arrival per softmax warp
+    mbar_init(&p_ready, 8);
     mbar_init(&p_free, 1);
     mbar_init(&o_done, 1);
     fence_mbar_init();
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
   } else {
     // ------------------------------------------------------------------ softmax + epilogue: thread <-> query row
     const int qd = warp & 3;                    // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;           // which half of a tile's keys (and of the output channels) this thread takes
     const int r = qd * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t p_base = smem_base + p.off_p;
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
       tcgen05_fence_after();
       const int valid = min(w1, p.n - j * w1);
 #pragma unroll 1
-      for (int ch = 0; ch < w1 / 32; ++ch) {
+      for (int ch = half * (w1 / 64); ch < (half + 1) * (w1 / 64); ++ch) {
         uint32_t v[32];
         attn_ld32(tmem_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
@@ -210,6 +214,10 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free);
     }
+    xch[half][r] = m;                           // the row maximum over both halves
+    named_bar_sync(1, 256);
+    m = fmaxf(xch[0][r], xch[1][r]);
+    named_bar_sync(1, 256);                     // (xch is reused for the row sums)
     // pass 2: p = exp(s - m), row sum, bf16 panels for the P V^T MMAs
     float l = 0.0f;
     for (int j = 0; j < T; ++j, ++sc) {
@@ -251,22 +259,15 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
         }
       };
       {
-        uint32_t va[32], vb[32];
-        attn_ld32(tmem_s + lane_sel, va);
+        uint32_t va[32], vb[32];                // this thread's 64 keys = panel `half`
+        attn_ld32(tmem_s + lane_sel + half * 64, va);
+        attn_ld32(tmem_s + lane_sel + half * 64 + 32, vb);
         tmem_ld_wait();
-        attn_ld32(tmem_s + lane_sel + 32, vb);
-        process(0, va);
-        tmem_ld_wait();
-        attn_ld32(tmem_s + lane_sel + 64, va);
-        process(1, vb);
-        tmem_ld_wait();
-        attn_ld32(tmem_s + lane_sel + 96, vb);
-        process(2, va);
-        tmem_ld_wait();
-        tcgen05_fence_before();                 // S has been read completely: hand it back before the last exponentials
+        tcgen05_fence_before();                 // S has been read completely: hand it back before the exponentials
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free);
-        process(3, vb);
+        process(2 * half, va);
+        process(2 * half + 1, vb);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -275,11 +276,14 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05(const __grid_c
     // epilogue: out = O / l + bias + x
     mbar_wait(&o_done, 0);
     tcgen05_fence_after();
+    xch[half][r] = l;
+    named_bar_sync(1, 256);
+    l = xch[0][r] + xch[1][r];
     const int q = q0 + r;
     const float inv = 1.0f / l;
     const size_t rowi = static_cast<size_t>(img) * p.n + q;
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.c; c0 += 32) {
+    for (int c0 = half * 32; c0 < p.c; c0 += 64) {          // 32-channel chunks alternate between the two halves
       uint32_t v[32];
       attn_ld32(tmem_o + lane_sel + c0, v);
       tmem_ld_wait();
