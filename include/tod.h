@@ -71,8 +71,17 @@ typedef struct tod_conv_desc {
   int32_t out_dtype;      /* TOD_OUT_* */
   int32_t block_k;        /* 0 = auto (64/32/16 from cin) */
   int32_t num_stages;     /* 0 = auto */
-  int32_t reserved[4];
+  int32_t reserved[4];    /* tools only: kernel variant, m, no resident weights, N-tile cap (tools/conv_bench.py) */
+  int32_t flags;          /* TOD_CONV_* bits below */
+  int32_t reserved2[3];
 } tod_conv_desc;
+
+/* d_w was written by an earlier kernel of the same stream (a GEMM whose "weights" are activations, e.g. q . k^T of
+ * SelfAttention, model/blocks.py:243-245): the kernel must not prefetch it ahead of the programmatic-launch wait. */
+#define TOD_CONV_DYNAMIC_W 1
+/* Walk the output tiles from the last image to the first.  Consecutive layers of the plan alternate direction so that a
+ * layer starts on the activations its producer wrote last, which are the ones still resident in the 126 MB L2. */
+#define TOD_CONV_REVERSE 2
 
 int tod_conv2d_nhwc_bf16(const tod_conv_desc* desc, void* stream);
 

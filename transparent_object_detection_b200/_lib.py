@@ -30,8 +30,11 @@ class ConvDesc(C.Structure):
         ("ksize", C.c_int32), ("stride", C.c_int32),
         ("x_pitch", C.c_int32), ("res_pitch", C.c_int32), ("out_pitch", C.c_int32),
         ("act", C.c_int32), ("out_dtype", C.c_int32), ("block_k", C.c_int32), ("num_stages", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("reserved", C.c_int32 * 4), ("flags", C.c_int32), ("reserved2", C.c_int32 * 3),
     ]
+
+
+TOD_CONV_DYNAMIC_W, TOD_CONV_REVERSE = 1, 2
 
 
 class DecodeDesc(C.Structure):

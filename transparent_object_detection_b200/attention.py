@@ -1,6 +1,8 @@
-"""Attention blocks of the reference's current-source backbone / head, block level: the
-same constructors, parameter names and call signature as model/blocks.py, evaluated by libtod.so on NHWC bf16.  They are
-not yet part of the captured network plan (DetectorEngine builds the plain topology).  No CPU fallback."""
+"""Attention blocks of the reference's current-source backbone / head: the same constructors,
+parameter names and call signature as model/blocks.py:190-254, evaluated by libtod.so on NHWC bf16.  These classes are the
+block-level drop-ins; inside the captured network plan (`BaseModel(..., attention=True)`) the engine issues the same C-ABI
+calls on its own pre-allocated buffers (engine.py:_cbam, _self_attention) and shares `_gemm` / `unfused_attention_image`
+with this module.  No CPU fallback."""
 from __future__ import annotations
 
 import ctypes as C
@@ -57,16 +59,32 @@ class CBAM(nn.Module):
 
 # ----------------------------------------------------------------------------------------------- SelfAttention
 def _gemm(L, st, x_ptr, h, w, cin, x_pitch, w_ptr, cout, out_ptr, out_pitch, out_f32=False, bias_ptr=None,
-          res_ptr=None, res_pitch=0, what="gemm"):
-    """D[h*w, cout] = A[h*w, cin] . W[cout, cin]^T (+ bias) (+ residual) through tod_conv2d_nhwc_bf16 as a 1x1 conv."""
-    from ._lib import ConvDesc, TOD_ACT_NONE, TOD_OUT_BF16, TOD_OUT_F32
+          res_ptr=None, res_pitch=0, what="gemm", dynamic_w=False):
+    """D[h*w, cout] = A[h*w, cin] . W[cout, cin]^T (+ bias) (+ residual) through tod_conv2d_nhwc_bf16 as a 1x1 conv.
+    dynamic_w: the "weight" operand is an activation written by an earlier kernel of the stream (k in q . k^T, x in
+    (gamma Wv) . x^T, v^T in P . v^T): the conv kernel must not prefetch it ahead of its programmatic-launch wait."""
+    from ._lib import ConvDesc, TOD_ACT_NONE, TOD_CONV_DYNAMIC_W, TOD_OUT_BF16, TOD_OUT_F32
     d = ConvDesc()
+    d.flags = TOD_CONV_DYNAMIC_W if dynamic_w else 0
     d.d_x, d.d_w, d.d_out = x_ptr, w_ptr, out_ptr
     d.d_bias, d.d_residual = bias_ptr, res_ptr
     d.batch, d.hin, d.win, d.cin, d.cout, d.ksize, d.stride = 1, h, w, cin, cout, 1, 1
     d.x_pitch, d.out_pitch, d.res_pitch = x_pitch, out_pitch, res_pitch
     d.act, d.out_dtype = TOD_ACT_NONE, (TOD_OUT_F32 if out_f32 else TOD_OUT_BF16)
     check(L.tod_conv2d_nhwc_bf16(C.byref(d), st), what)
+
+
+def unfused_attention_image(L, st, xi, h, w, Cc, d16, wq, bq, wk, bk, wv, bv, qi, ki, S, P, vT, out_i):
+    """One image of the unfused SelfAttention chain (model/blocks.py:239-253) on raw device pointers: q / k projections,
+    S = q k^T (f32, N x N), row softmax -> P (bf16), vT = (gamma Wv) x^T, out = P vT^T + gamma bv + x."""
+    N = h * w
+    _gemm(L, st, xi, h, w, Cc, Cc, wq, d16, qi, d16, bias_ptr=bq, what="query")
+    _gemm(L, st, xi, h, w, Cc, Cc, wk, d16, ki, d16, bias_ptr=bk, what="key")
+    _gemm(L, st, qi, h, w, d16, d16, ki, N, S, N, out_f32=True, what="scores", dynamic_w=True)
+    check(L.tod_softmax_rows_f32_bf16(S, P, N, N, N, N, st), "softmax")
+    _gemm(L, st, wv, 1, Cc, Cc, Cc, xi, N, vT, N, what="value^T", dynamic_w=True)
+    _gemm(L, st, P, h, w, N, N, vT, Cc, out_i, Cc, bias_ptr=bv, res_ptr=xi, res_pitch=Cc, what="attention output",
+          dynamic_w=True)
 
 
 def self_attention_fused_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: float) -> torch.Tensor:
@@ -157,14 +175,9 @@ def self_attention_nhwc(x: torch.Tensor, wq, bq, wk, bk, wv, bv, gamma: float) -
         st = torch.cuda.current_stream(dev).cuda_stream
         for i in range(B):
             xi = x.data_ptr() + i * N * Cc * 2
-            qi, ki = q.data_ptr() + i * N * d16 * 2, k.data_ptr() + i * N * d16 * 2
-            _gemm(L, st, xi, H, W, Cc, Cc, wq_p.data_ptr(), d16, qi, d16, bias_ptr=bq_p.data_ptr(), what="query")
-            _gemm(L, st, xi, H, W, Cc, Cc, wk_p.data_ptr(), d16, ki, d16, bias_ptr=bk_p.data_ptr(), what="key")
-            _gemm(L, st, qi, H, W, d16, d16, ki, N, S.data_ptr(), N, out_f32=True, what="scores")
-            check(L.tod_softmax_rows_f32_bf16(S.data_ptr(), P.data_ptr(), N, N, N, N, st), "softmax")
-            _gemm(L, st, wv_g.data_ptr(), 1, Cc, Cc, Cc, xi, N, vT.data_ptr(), N, what="value^T")
-            _gemm(L, st, P.data_ptr(), H, W, N, N, vT.data_ptr(), Cc, out.data_ptr() + i * N * Cc * 2, Cc,
-                  bias_ptr=bv_g.data_ptr(), res_ptr=xi, res_pitch=Cc, what="attention output")
+            unfused_attention_image(L, st, xi, H, W, Cc, d16, wq_p.data_ptr(), bq_p.data_ptr(), wk_p.data_ptr(), bk_p.data_ptr(),
+                                    wv_g.data_ptr(), bv_g.data_ptr(), q.data_ptr() + i * N * d16 * 2, k.data_ptr() + i * N * d16 * 2,
+                                    S.data_ptr(), P.data_ptr(), vT.data_ptr(), out.data_ptr() + i * N * Cc * 2)
         torch.cuda.current_stream(dev).synchronize()      # the temporaries above are freed on return
     return out
 

@@ -49,7 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "tod.h"))
-    objs = []
+    objs, jobs = [], []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
@@ -59,8 +59,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
-                print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
+
+    def compile_one(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    if jobs:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            list(pool.map(compile_one, jobs))
     if force or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
         if verbose:

@@ -331,11 +331,14 @@ extern "C" int tod_attention_fused(const tod_attention_desc* d, void* stream) {
   TOD_CHECK_ARG(d->d16 == 16 || d->d16 == 32 || d->d16 == 64, "attention: q/k width %d (16, 32 or 64)", d->d16);
   TOD_CHECK_ARG(d->c >= 32 && d->c % 32 == 0 && d->c <= 256, "attention: channels %d (multiple of 32, <= 256)", d->c);
   TOD_CHECK_ARG(d->x_pitch >= d->c && d->out_pitch >= d->c && d->x_pitch % 8 == 0 && d->out_pitch % 8 == 0, "attention: pitches");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  static PerDeviceOnce attr_once;   // the attribute is per device
   int rc;
-  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(attention_tcgen05)")) != TOD_OK) return rc;
+  if (attr_once.needed()) {
+    if ((rc = check_cuda(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                         "cudaFuncSetAttribute(attention_tcgen05)")) != TOD_OK)
+      return rc;
+    attr_once.done();
+  }
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const int rb = d->d16 * 2;

@@ -76,6 +76,8 @@ struct __align__(64) HaloParams {
   FastDiv fd_tiles_per_img, fd_tiles_w, fd_wout, fd_hw;
   long long mtot;            // batch * hout * wout
   int num_subtiles, m, num_super;
+  int reverse;               // TOD_CONV_REVERSE: sub-tile s stands for sub-tile num_subtiles - 1 - s (last image first)
+  int dyn_w;                 // TOD_CONV_DYNAMIC_W: the weights are an earlier kernel's output (no prefetch before pdl_wait)
   int n_tiles, block_n, cout;
   int block_k, ksteps, chunks, num_taps;
   // A loads per (sub-tile, chunk)
@@ -369,7 +371,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     if (elect_one()) {
       WaitClock wc(p.prof != nullptr);
       const long long role_t0 = wc.begin();
-      if (p.stationary) {
+      auto load_resident_weights = [&]() {
 #pragma unroll 1
         for (int c = 0; c < p.chunks; ++c)
 #pragma unroll 1
@@ -378,7 +380,9 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
             mbar_arrive_expect_tx(&b_full[i], p.b_tx_bytes);
             tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, (t * p.chunks + c) * p.block_k, n0);
           }
-      }
+      };
+      // constant weights do not depend on earlier kernels: requested before the programmatic-launch wait
+      if (p.stationary && !p.dyn_w) load_resident_weights();
       if (TAIL) {
         mbar_arrive_expect_tx(&w2_full_bar, 64u * 128u);
         tma_load_2d(&p.tm_w2, &w2_full_bar, smem_base + p.off_w2, 0, 0);
@@ -387,6 +391,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       // and upsample-add operands and the output buffer are not: every access to them in this grid is ordered after
       // this wait through the mbarrier chain that starts at the first A load below.
       pdl_wait();
+      if (p.stationary && p.dyn_w) load_resident_weights();   // "weights" produced by the previous kernel (q . k^T)
       int ai = 0, bi = 0;
       uint32_t pha = 0, phb = 0;   // ring phase bits
       const int n_it = sched.iters();
@@ -403,7 +408,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
           const uint32_t slot = smem_base + ai * p.a_slot_bytes;
 #pragma unroll 1
           for (int mt = 0; mt < m_cur; ++mt) {
-            const int s = s0 + mt;
+            const int s = p.reverse ? p.num_subtiles - 1 - (s0 + mt) : s0 + mt;
             int c1, c2, c3;
             if (p.patch_mode) {
               const int img = p.fd_tiles_per_img.div(s);
@@ -656,7 +661,8 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         tcgen05_fence_after();
 #pragma unroll 1
         for (int mt = 0; mt < m_cur; ++mt) {
-          const long long pix = static_cast<long long>(s0 + mt) * 128 + r;
+          const int sr = p.reverse ? p.num_subtiles - 1 - (s0 + mt) : s0 + mt;
+          const long long pix = static_cast<long long>(sr) * 128 + r;
           const bool valid = pix < p.mtot;
           const int ipix = valid ? static_cast<int>(pix) : 0;
           const int img = p.fd_hw.div(ipix);
@@ -746,8 +752,9 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       }
     } else {
     // tile coordinates of sub-tile s and this thread's row of the extra operand (null: row outside the tensor)
-    auto locate = [&](int s, int& c1, int& c2, int& c3, const void*& ex_row) {
+    auto locate = [&](int s_sched, int& c1, int& c2, int& c3, const void*& ex_row) {
       ex_row = nullptr;
+      const int s = p.reverse ? p.num_subtiles - 1 - s_sched : s_sched;
       if (p.patch_mode) {
         const int img = p.fd_tiles_per_img.div(s);
         const int rem = s - img * p.tiles_per_img;
@@ -1042,6 +1049,8 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
       bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   const uint64_t px = static_cast<uint64_t>(d->x_pitch) * 2;
   const long long mtot = static_cast<long long>(d->batch) * hout * wout;
+  // (stride 2: the four parity planes of a tile together read every pixel, so the pitch that matters is still one pixel)
+  const CUtensorMapL2promotion promo_in = l2_promotion_for(static_cast<uint64_t>(d->cin) * 2, px);
 
   p.hout = hout;
   p.wout = wout;
@@ -1067,7 +1076,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(mtot), 1, 1};
     const uint64_t str[3] = {px, px * mtot, px * mtot};
     const uint32_t box[4] = {static_cast<uint32_t>(bk), rows, 1, 1};
-    if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+    if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
     p.n_aloads = 1;
     p.al_map[0] = 0;
     p.a_tx_bytes = rows * rb;
@@ -1089,7 +1098,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
                                 static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
       const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
       const uint32_t box[4] = {static_cast<uint32_t>(bk), kPatchW, kPatchH, 1};
-      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
       p.n_aloads = 1;
       p.al_map[0] = 0;
       p.a_tx_bytes = 128 * rb;
@@ -1102,7 +1111,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
                                 static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
       const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
       const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(pw), static_cast<uint32_t>(ph), 1};
-      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
       p.n_aloads = 1;
       p.al_map[0] = 0;
       p.al_dw[0] = -1;
@@ -1130,7 +1139,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
           const int bw = kPatchW + pw, bh = kPatchH + ph;
           const uint8_t* base = reinterpret_cast<const uint8_t*>(d->d_x) + (static_cast<uint64_t>(ph) * d->win + pw) * px;
           const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1};
-          if ((rc = encode_map(&p.tm_a[n], base, 4, dims, str, box, swz_in)) != TOD_OK) return rc;
+          if ((rc = encode_map(&p.tm_a[n], base, 4, dims, str, box, swz_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
           p.al_map[n] = n;
           p.al_dw[n] = -pw;
           p.al_dh[n] = -ph;
@@ -1222,19 +1231,20 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     const CUtensorMapSwizzle swz_res =
         p.pb >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     const uint64_t rpx = static_cast<uint64_t>(d->res_pitch) * 2;
+    const CUtensorMapL2promotion promo_res = l2_promotion_for(static_cast<uint64_t>(d->cout) * 2, rpx);
     if (p.patch_mode) {
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(wout), static_cast<uint64_t>(hout),
                                 static_cast<uint64_t>(d->batch)};
       const uint64_t str[3] = {rpx, rpx * wout, rpx * wout * hout};
       const uint32_t box[4] = {static_cast<uint32_t>(p.pc), kPatchW, kPatchH, 1};
-      if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res)) != TOD_OK) return rc;
+      if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_res)) != TOD_OK) return rc;
       p.res_tx_bytes = static_cast<uint32_t>(p.pb) * kPatchW * kPatchH;
     } else {
       const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(mtot), 1, 1};
       const uint64_t str[3] = {rpx, rpx * mtot, rpx * mtot};
       const uint32_t box[4] = {static_cast<uint32_t>(p.pc), rows, 1, 1};
-      if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res)) != TOD_OK) return rc;
+      if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_res)) != TOD_OK) return rc;
       p.res_tx_bytes = static_cast<uint32_t>(p.pb) * rows;
     }
   }
@@ -1321,6 +1331,8 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.upadd = d->d_upadd;
   p.res_pitch = d->res_pitch;
   p.act = d->act;
+  p.reverse = (d->flags & TOD_CONV_REVERSE) ? 1 : 0;
+  p.dyn_w = (d->flags & TOD_CONV_DYNAMIC_W) ? 1 : 0;
   p.prof = g_prof;
   *smem_bytes = smem;
   return TOD_OK;
@@ -1351,14 +1363,15 @@ static HaloKernel halo_kernel(int i) {
 }
 
 int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_desc* fuse) {
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    for (int i = 0; i < kHaloVariants - 2 && attr_err == cudaSuccess; ++i)   // (the tail variants set their own, smaller limit)
-      attr_err = cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit);
-  });
+  static PerDeviceOnce attr_once;   // the attribute is per device
   int rc;
-  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_halo_tcgen05)")) != TOD_OK) return rc;
+  if (attr_once.needed()) {
+    for (int i = 0; i < kHaloVariants - 2; ++i)   // (the tail variants set their own, smaller limit)
+      if ((rc = check_cuda(cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit),
+                           "cudaFuncSetAttribute(conv_halo_tcgen05)")) != TOD_OK)
+        return rc;
+    attr_once.done();
+  }
   const bool silu = d->act == TOD_ACT_SILU, f32 = d->out_dtype == TOD_OUT_F32;
   const int extra = d->d_residual != nullptr ? 1 : (d->d_upadd != nullptr ? 2 : 0);
   TOD_CHECK_ARG(!(d->d_residual != nullptr && d->d_upadd != nullptr), "conv: residual and upsample-add are mutually exclusive");
@@ -1426,14 +1439,15 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
 
 // Conv (64 output channels, SiLU) + a 1x1 conv 64 -> 64 (SiLU) on its output, the intermediate kept on chip (EXTRA 7).
 int conv_halo_launch_tail(const tod_conv_desc* d, const tod_conv_tail_desc* t, void* stream, const tod_head_fuse_desc* fuse) {
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    for (int i = 12; i <= 13 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit - 1024);
-  });
+  static PerDeviceOnce attr_once;
   int rc;
-  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_halo_tcgen05 tail)")) != TOD_OK) return rc;
+  if (attr_once.needed()) {
+    for (int i = 12; i <= 13; ++i)
+      if ((rc = check_cuda(cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit - 1024),
+                           "cudaFuncSetAttribute(conv_halo_tcgen05 tail)")) != TOD_OK)
+        return rc;
+    attr_once.done();
+  }
   TOD_CHECK_ARG(t != nullptr && t->d_w2 != nullptr && (t->d_out2 != nullptr || fuse != nullptr), "conv tail: null pointer");
   TOD_CHECK_ARG(d->cout == 64 && t->cout2 == 64, "conv tail: needs 64 -> 64 (got %d -> %d)", d->cout, t->cout2);
   TOD_CHECK_ARG(d->act == TOD_ACT_SILU && t->act2 == (fuse ? TOD_ACT_NONE : TOD_ACT_SILU),

@@ -48,6 +48,7 @@ struct __align__(64) ConvKernelParams {
   int res_pitch, out_pitch;
   int up_h, up_w;          // real output dims for the upsample-add (flat mode needs them)
   int act, out_f32;
+  int reverse;             // TOD_CONV_REVERSE: walk the tiles from the last to the first
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t desc_hi) {
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
       pdl_wait();
       int s = 0;         // ring slot and phase, continue across tiles
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile_i = blockIdx.x; tile_i < p.total_tiles; tile_i += gridDim.x) {
+        const int tile = p.reverse ? p.total_tiles - 1 - tile_i : tile_i;
         const int mt = tile / p.n_tiles;
         const int n0 = (tile - mt * p.n_tiles) * p.block_n;
         const int img = mt / tiles_per_img;
@@ -230,8 +232,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
     const int ptw = r - pth * p.tw;
     const bool in_patch = r < p.th * p.tw;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile_i = blockIdx.x; tile_i < p.total_tiles; tile_i += gridDim.x, ++lt) {
       if ((lt & 1) != static_cast<uint32_t>(group)) continue;
+      const int tile = p.reverse ? p.total_tiles - 1 - tile_i : tile_i;
       const int mt = tile / p.n_tiles;
       const int n0 = (tile - mt * p.n_tiles) * p.block_n;
       const int img = mt / tiles_per_img;
@@ -442,12 +445,13 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
     variant = halo ? 2 : 1;
   }
   if (variant == 2) return conv_halo_launch(d, stream);
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-  });
-  if ((rc = check_cuda(attr_err, "cudaFuncSetAttribute(conv_igemm_tcgen05)")) != TOD_OK) return rc;
+  static PerDeviceOnce attr_once;   // the attribute is per device
+  if (attr_once.needed()) {
+    if ((rc = check_cuda(cudaFuncSetAttribute(conv_igemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit),
+                         "cudaFuncSetAttribute(conv_igemm_tcgen05)")) != TOD_OK)
+      return rc;
+    attr_once.done();
+  }
 
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
@@ -472,6 +476,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   p.chunks_per_tap = cin_pad / bk;
 
   const uint64_t px = static_cast<uint64_t>(d->x_pitch) * 2;  // bytes per input pixel
+  const CUtensorMapL2promotion promo_in = l2_promotion_for(static_cast<uint64_t>(d->cin) * 2, px);
   if (d->ksize == 1) {
     // flat: 128 consecutive pixels per tile
     const long long mtot = static_cast<long long>(d->batch) * d->hin * d->win;
@@ -484,7 +489,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
     const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(mtot), 1, 1};
     const uint64_t str[3] = {px, px * mtot, px * mtot};
     const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.tw), 1, 1};
-    if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz)) != TOD_OK) return rc;
+    if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
     p.tap_map[0] = 0;
   } else {
     p.hout = hout;
@@ -497,7 +502,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
                                 static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
       const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
-      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz)) != TOD_OK) return rc;
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) {
           p.tap_map[kh * 3 + kw] = 0;
@@ -512,7 +517,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
           const uint8_t* base = reinterpret_cast<const uint8_t*>(d->d_x) + (static_cast<uint64_t>(ph) * d->win + pw) * px;
-          if ((rc = encode_map(&p.tm_a[ph * 2 + pw], base, 4, dims, str, box, swz)) != TOD_OK) return rc;
+          if ((rc = encode_map(&p.tm_a[ph * 2 + pw], base, 4, dims, str, box, swz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
         }
       const int par[3] = {1, 0, 1}, off[3] = {-1, 0, 0};
       for (int kh = 0; kh < 3; ++kh)
@@ -566,6 +571,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   p.up_w = wout;
   p.act = d->act;
   p.out_f32 = d->out_dtype == TOD_OUT_F32;
+  p.reverse = (d->flags & TOD_CONV_REVERSE) ? 1 : 0;
 
   const long long m_tiles = static_cast<long long>(d->ksize == 1 ? 1 : d->batch) * p.tiles_h * p.tiles_w;
   p.n_tiles = ceil_div(d->cout, block_n);

@@ -248,12 +248,12 @@ extern "C" int tod_head_decode(const tod_decode_desc* d, void* stream) {
   p.cand_cls = d->d_cand_cls;
   const bool full_out = d->d_head_out != nullptr || d->d_decoded != nullptr;
   const size_t smem = full_out ? (static_cast<size_t>(kDecAnchors) * (d->nc + 1) + kDecAnchors * 4) * sizeof(float) : 0;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;   // the attribute is per device
+  if (attr_once.needed()) {
     int rc = check_cuda(cudaFuncSetAttribute(head_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                         "cudaFuncSetAttribute(head_decode)");
     if (rc != TOD_OK) return rc;
-    attr_done = true;
+    attr_once.done();
   }
   TOD_CHECK_ARG(smem <= 200 * 1024, "decode: nc %d too large for shared memory", d->nc);
   dim3 grid(total_tiles, d->batch, 1);

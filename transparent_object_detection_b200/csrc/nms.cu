@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
   __syncthreads();
   for (int i = threadIdx.x; i < anchors; i += kSortThreads) {
     const float s = conf[i];
-    if (s >= conf_thres) {
+    // class ids outside [0, 4096) do not fit the key's 12 class bits (they would reorder the segments silently):
+    // such a row -- e.g. the 0x7fffffff of an all-NaN score row -- is never a candidate
+    if (s >= conf_thres && static_cast<unsigned>(cls[i]) < 4096u) {
       const int pos = atomicAdd(&s_count, 1);
       keys[pos] = (static_cast<unsigned long long>(cls[i]) << (kIdxBits + kScoreBits)) |
                   (static_cast<unsigned long long>(score_desc_bits(s)) << kIdxBits) | static_cast<unsigned long long>(i);
@@ -474,6 +476,7 @@ extern "C" int tod_nms_prepare_dense(float* d_prediction, int32_t batch, int32_t
                                      float* d_cand_box, float* d_cand_conf, int32_t* d_cand_cls, void* stream) {
   TOD_CHECK_ARG(d_prediction && d_cand_box && d_cand_conf && d_cand_cls, "nms_prepare_dense: null pointer");
   TOD_CHECK_ARG(batch > 0 && anchors > 0 && nc > 0, "nms_prepare_dense: bad shape");
+  TOD_CHECK_ARG(nc <= 4096, "nms_prepare_dense: nc %d exceeds the 4096 classes the sort key holds", nc);
   TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d_cand_box) & 15) == 0, "nms_prepare_dense: cand_box not 16-byte aligned");
   const long long rows = static_cast<long long>(batch) * anchors;
   const long long blocks = (rows * 32 + 255) / 256;
@@ -507,13 +510,13 @@ extern "C" int tod_nms(const float* d_cand_box, const float* d_cand_conf, const 
   auto st = static_cast<cudaStream_t>(stream);
   const int ap2 = next_pow2(anchors);
   const size_t sort_smem = wk.keys_g ? 0 : static_cast<size_t>(ap2) * 8;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;   // the attribute is per device
+  if (attr_once.needed()) {
     int rc = check_cuda(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kSortSmemKeys * 8),
                         "cudaFuncSetAttribute(nms_sort)");
     if (rc != TOD_OK) return rc;
-    attr_done = true;
+    attr_once.done();
   }
   nms_sort_kernel<<<batch, kSortThreads, sort_smem, st>>>(d_cand_conf, d_cand_cls, anchors, conf_thres, wk, ap2);
   TOD_CHECK_LAUNCH("nms_sort_kernel launch");

@@ -139,15 +139,15 @@ extern "C" int tod_sppf_pool_nhwc_bf16(void* d_buf, int32_t batch, int32_t h, in
   TOD_CHECK_ARG(batch > 0 && h > 0 && w > 0, "sppf_pool: bad shape");
   TOD_CHECK_ARG(c > 0 && c % 8 == 0 && pitch >= 4 * c && pitch % 8 == 0, "sppf_pool: c %d pitch %d", c, pitch);
   TOD_CHECK_ARG((reinterpret_cast<uintptr_t>(d_buf) & 15) == 0, "sppf_pool: buffer must be 16-byte aligned");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;   // the attribute is per device
+  if (attr_once.needed()) {
     int rc = check_cuda(cudaFuncSetAttribute(sppf_pool_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                         "cudaFuncSetAttribute(sppf_pool<2>)");
     if (rc != TOD_OK) return rc;
     rc = check_cuda(cudaFuncSetAttribute(sppf_pool_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                     "cudaFuncSetAttribute(sppf_pool<1>)");
     if (rc != TOD_OK) return rc;
-    attr_done = true;
+    attr_once.done();
   }
   const size_t plane16 = static_cast<size_t>(h) * w * 16;  // bytes for one 8-channel vector plane
   auto st = static_cast<cudaStream_t>(stream);

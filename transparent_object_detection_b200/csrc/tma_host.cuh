@@ -29,7 +29,8 @@ inline EncodeTiledFn get_encode_fn() {
 // dims / box are innermost first; strides_bytes[i] is the byte stride of dimension i+1.
 inline int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, CUtensorMapSwizzle swz,
-                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -45,7 +46,7 @@ inline int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(map, dtype, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] "
               "stride0 %llu base %p",
@@ -83,15 +84,36 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-inline int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+// L2 promotion (the granularity at which a TMA load's misses are fetched into L2) for a tensor whose innermost box covers
+// `window_bytes` of a `pitch_bytes` pixel: a channel WINDOW of a wider concat buffer (C2f's chunk / bottleneck inputs,
+// model/blocks.py:104-108) must not be promoted past its own width, or every miss drags the neighbouring windows' bytes
+// out of DRAM as well (ncu, round 1: 2.0x the algorithmic DRAM reads on the 32-of-96-channel layers at 160^2).
+// TOD_L2PROMO=256 restores the fixed 256-byte promotion for A/B measurements.
+inline CUtensorMapL2promotion l2_promotion_for(uint64_t window_bytes, uint64_t pitch_bytes) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TOD_L2PROMO");
+    mode = (e != nullptr) ? atoi(e) : 0;
   }
-  return sms;
+  if (window_bytes >= pitch_bytes || mode == 256) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;   // dense tensor
+  if (mode == 128) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (mode == 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+  if (mode == 1) return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  if (window_bytes >= 256) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (window_bytes >= 128) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (window_bytes >= 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+  return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
+inline int num_sms() {
+  static int sms[64] = {0};
+  const int dev = current_device_index();
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
+  }
+  return sms[dev];
 }
 
 inline int pick_block_k(int cin, int hint) {

@@ -28,6 +28,20 @@ int check_cuda(cudaError_t e, const char* what);
     if (_rc != TOD_OK) return _rc;                              \
   } while (0)
 
+// cudaFuncSetAttribute and the SM count are per DEVICE, and one process may drive several GPUs (BaseModel.engine(device=)):
+// one-time setup is therefore keyed by the current device.  Returns true until mark_device_ready() has been called for it;
+// two threads racing through the (idempotent) setup is harmless.
+inline int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 0;
+  return dev;
+}
+struct PerDeviceOnce {
+  unsigned long long ready = 0;   // bit per device ordinal
+  bool needed() const { return ((__atomic_load_n(&ready, __ATOMIC_ACQUIRE) >> current_device_index()) & 1ull) == 0; }
+  void done() { __atomic_fetch_or(&ready, 1ull << current_device_index(), __ATOMIC_RELEASE); }
+};
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -23,8 +23,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (CbamDesc, ConvDesc, ConvTailDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16,
-                   TOD_OUT_F32, check)
+from ._lib import (CbamDesc, ConvDesc, ConvTailDesc, DecodeDesc, HeadFuseDesc, TOD_ACT_NONE, TOD_ACT_SILU, TOD_CONV_REVERSE,
+                   TOD_FUSE_BOX, TOD_FUSE_CLS, TOD_OUT_BF16, TOD_OUT_F32, check)
 
 BN_EPS = 1e-5
 
@@ -204,7 +204,7 @@ class DetectorEngine:
         self.conv_flops += 2 * self.batch * (2 * N * d16 * Cc + N * N * d16 + N * Cc * Cc + N * N * Cc)
 
     def _run_attention(self, plan: dict, st: int) -> None:
-        from .attention import _gemm
+        from .attention import _gemm, unfused_attention_image
         L, v, N, Cc, d16 = self.L, plan["v"], plan["N"], plan["C"], plan["d16"]
         if plan["fused"]:
             from ._lib import AttentionDesc
@@ -223,14 +223,10 @@ class DetectorEngine:
             return
         for i in range(self.batch):
             xi = v.ptr + i * N * Cc * 2
-            qi, ki = plan["q"].data_ptr() + i * N * d16 * 2, plan["k"].data_ptr() + i * N * d16 * 2
-            _gemm(L, st, xi, v.h, v.w, Cc, Cc, plan["wq"].data_ptr(), d16, qi, d16, bias_ptr=plan["bq"].data_ptr(), what="query")
-            _gemm(L, st, xi, v.h, v.w, Cc, Cc, plan["wk"].data_ptr(), d16, ki, d16, bias_ptr=plan["bk"].data_ptr(), what="key")
-            _gemm(L, st, qi, v.h, v.w, d16, d16, ki, N, plan["S"].data_ptr(), N, out_f32=True, what="scores")
-            check(L.tod_softmax_rows_f32_bf16(plan["S"].data_ptr(), plan["P"].data_ptr(), N, N, N, N, st), "softmax")
-            _gemm(L, st, plan["wv"].data_ptr(), 1, Cc, Cc, Cc, xi, N, plan["vT"].data_ptr(), N, what="value^T")
-            _gemm(L, st, plan["P"].data_ptr(), v.h, v.w, N, N, plan["vT"].data_ptr(), Cc, xi, Cc,
-                  bias_ptr=plan["bv"].data_ptr(), res_ptr=xi, res_pitch=Cc, what="attention output")
+            unfused_attention_image(L, st, xi, v.h, v.w, Cc, d16, plan["wq"].data_ptr(), plan["bq"].data_ptr(),
+                                    plan["wk"].data_ptr(), plan["bk"].data_ptr(), plan["wv"].data_ptr(), plan["bv"].data_ptr(),
+                                    plan["q"].data_ptr() + i * N * d16 * 2, plan["k"].data_ptr() + i * N * d16 * 2,
+                                    plan["S"].data_ptr(), plan["P"].data_ptr(), plan["vT"].data_ptr(), xi)
 
     def _conv_bn(self, sd, prefix: str, src: View, dst: View, stride: int = 1, residual: Optional[View] = None) -> None:
         w, b = fold_conv_bn(sd, prefix)
@@ -323,12 +319,22 @@ class DetectorEngine:
         ncp = (nc + 15) // 16 * 16           # class conv output padded to the MMA N granularity
         self.raw_pitch = 64 + ncp
         self.raw: List[torch.Tensor] = []
+        fuse_head0 = os.environ.get("TOD_FUSE_HEAD0", "0") == "1" and not self.attention   # (a CBAM follows each .0 otherwise)
         for i, f in enumerate(feats):
             raw = torch.zeros((B, f.h, f.w, self.raw_pitch), dtype=torch.float32, device=dev)
             self.raw.append(raw)
             rv = View(raw, 0, self.raw_pitch)
-            tb1, tb2 = self._buf(f.h, f.w, c2), self._buf(f.h, f.w, c2)
-            self._conv_bn(sd, f"head.box.{i}.0", f, tb1)
+            tb2 = self._buf(f.h, f.w, c2)
+            if fuse_head0:
+                # box.i.0 and cls.i.0 read the same feature map (model/head.py:26,37): ONE conv with the two weight sets
+                # stacked along cout writes [box c2 | cls c1] and the towers' second convs read channel windows of it
+                t01 = self._buf(f.h, f.w, c2 + c1)
+                tb1, tc1 = t01.sub(0, c2), t01.sub(c2, c1)
+                (wb_, bb_), (wc_, bc_) = fold_conv_bn(sd, f"head.box.{i}.0"), fold_conv_bn(sd, f"head.cls.{i}.0")
+                self._conv(f"head.boxcls.{i}.0", torch.cat([wb_, wc_]), torch.cat([bb_, bc_]), f, t01)
+            else:
+                tb1, tc1 = self._buf(f.h, f.w, c2), self._buf(f.h, f.w, c1)
+                self._conv_bn(sd, f"head.box.{i}.0", f, tb1)
             if self.attention:
                 self._cbam(sd, f"head.box.{i}.1", tb1)
             self._conv_bn(sd, f"head.box.{i}.2", tb1, tb2)
@@ -336,8 +342,9 @@ class DetectorEngine:
                 self._cbam(sd, f"head.box.{i}.3", tb2)
             self._conv(f"head.box.{i}.4", _t(sd, f"head.box.{i}.4.weight"), _t(sd, f"head.box.{i}.4.bias"), tb2,
                        rv.sub(0, 64), act=TOD_ACT_NONE, out_f32=True)
-            tc1, tc2 = self._buf(f.h, f.w, c1), self._buf(f.h, f.w, c1)
-            self._conv_bn(sd, f"head.cls.{i}.0", f, tc1)
+            tc2 = self._buf(f.h, f.w, c1)
+            if not fuse_head0:
+                self._conv_bn(sd, f"head.cls.{i}.0", f, tc1)
             if self.attention:
                 self._cbam(sd, f"head.cls.{i}.1", tc1)
             self._conv_bn(sd, f"head.cls.{i}.2", tc1, tc2)
@@ -406,6 +413,33 @@ class DetectorEngine:
                     t.cout2, t.out2_pitch, t.act2 = 64, 64, TOD_ACT_NONE
                     self.tail_box[na] = (t, self.head_fuse[nb])
                     self.tail_box_skip.add(nb)
+
+        if os.environ.get("TOD_SNAKE", "1") != "0":
+            self._assign_tile_order()
+
+    def _assign_tile_order(self) -> None:
+        """Consecutive convs walk the batch in opposite directions (TOD_CONV_REVERSE on every other one): a layer then starts
+        on the images its producer wrote LAST, which are the ones still in the 126 MB L2 (a batch-64 activation at 160^2 or
+        80^2 is 105-420 MB, so a same-direction consumer always starts on evicted lines).  The stem writes first-to-last."""
+        rev, direction = False, {}
+        for kind, name, payload in self.ops:
+            if kind != "conv" or name.startswith("head.") or name in self.tail_skip:
+                continue
+            rev = not rev
+            payload.flags = (payload.flags | TOD_CONV_REVERSE) if rev else (payload.flags & ~TOD_CONV_REVERSE)
+            direction[name] = rev
+        for lvl, feat in enumerate(("neck.h2.cv2", "neck.h4.cv2", "neck.h6.cv2")):
+            base = direction.get(feat, False)
+            for kind, name, payload in self.ops:
+                if kind == "conv" and name.startswith(f"head.boxcls.{lvl}."):
+                    base = not base
+                    payload.flags = (payload.flags | TOD_CONV_REVERSE) if base else (payload.flags & ~TOD_CONV_REVERSE)
+            for tower in ("box", "cls"):
+                r = base
+                for kind, name, payload in self.ops:
+                    if kind == "conv" and name.startswith(f"head.{tower}.{lvl}."):
+                        r = not r
+                        payload.flags = (payload.flags | TOD_CONV_REVERSE) if r else (payload.flags & ~TOD_CONV_REVERSE)
 
     # ------------------------------------------------------------------ execution
     def _stream(self) -> int:
@@ -488,7 +522,8 @@ class DetectorEngine:
                 continue
             ready = torch.cuda.Event()
             ready.record(main)
-            for tower in ("box", "cls"):
+            shared = [(k2, n2, p2) for k2, n2, p2 in self.ops if n2.startswith(f"head.boxcls.{lvl}.")]   # TOD_FUSE_HEAD0
+            for tower in ("cls", "box") if shared else ("box", "cls"):
                 # stream priorities become kernel-node priorities in the captured graph: the big level-0 towers are
                 # throughput work that fills gaps, the small deep-level towers are the tail of the critical path
                 if (tower, lvl) not in self._side_streams:
@@ -496,6 +531,11 @@ class DetectorEngine:
                     self._side_streams[(tower, lvl)] = torch.cuda.Stream(self.device, priority=prio)
                 side = self._side_streams[(tower, lvl)]
                 side.wait_event(ready)
+                if shared and tower == "cls":          # the stacked first conv runs on the class tower's stream ...
+                    for k2, n2, p2 in shared:
+                        issue(k2, n2, p2, side)
+                    ready = torch.cuda.Event()         # ... and the box tower starts after it
+                    ready.record(side)
                 prefix = f"head.{tower}.{lvl}."
                 for k2, n2, p2 in self.ops:
                     if n2.startswith(prefix):
