@@ -189,7 +189,7 @@ def main():
         args.warmup = 3
 
     import torch.distributed as dist
-    from oracle import synth
+    from transparent_object_detection_b200 import synth
     from transparent_object_detection_b200 import BaseModel, Detector
 
     torch.cuda.set_device(local_rank)

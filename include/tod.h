@@ -213,6 +213,19 @@ int tod_decode_box_from_head(const float* d_head_out, float* d_decoded, int32_t 
                              int32_t in_h, int32_t in_w, void* stream);
 
 /*
+ * DecodeBox.decode_box on the upstream 5-tuple the reference's callers are written for (utils/bbox_utils.py:66-82;
+ * callers utils/callbacks.py:150-151, dataset/coco/get_map.py:68-69): (dbox, cls, origin_cls, anchors, strides) ->
+ * d_decoded f32 [batch, A, 4+nc] = cat(dist2bbox(dbox, anchors, xywh) * strides, sigmoid(cls)).permute(0, 2, 1) with
+ * xywh / (in_w, in_h, in_w, in_h).  Box columns are bit-exact with the reference (same float32 operation order);
+ * origin_cls is unused by the reference as well.
+ *   d_dbox f32 [batch, 4, A] (DFL distances l, t, r, b in grid units), d_cls f32 [batch, nc, A] (logits),
+ *   d_anchors f32 [2, A] (x row, y row: make_anchors(...)[0].transpose(0, 1), model/head.py:53), d_strides f32 [A]
+ */
+int tod_decode_box_from_tuple(const float* d_dbox, const float* d_cls, const float* d_anchors, const float* d_strides,
+                              float* d_decoded, int32_t batch, int32_t nc, int32_t anchors, int32_t in_h, int32_t in_w,
+                              void* stream);
+
+/*
  * NMS, step 0 (only for the dense reference-layout tensor): xywh -> corners IN PLACE on
  * d_prediction f32 [batch, A, 4+nc] (the reference's side effect, utils/bbox_utils.py:144-149) and class max.
  * Replaces utils/bbox_utils.py:144-153.
@@ -250,6 +263,23 @@ int tod_nms(const float* d_cand_box, const float* d_cand_conf, const int32_t* d_
  */
 int tod_correct_boxes(const float* d_dets, const int32_t* d_keep_count, int32_t batch, int32_t anchors,
                       const double* d_params, int32_t letterbox, float* d_rows, void* stream);
+
+/*
+ * Result packing + top-`max_boxes` on the device: the batch's kept rows compacted image after
+ * image, so that one small device-to-host copy carries every detection.
+ * Replaces: the per-image `.cpu().numpy()` of utils/bbox_utils.py:178 and, with max_boxes > 0, the top-k of the reference's
+ *           detect loop, utils/callbacks.py:159-166 (`np.argsort(top_conf)[::-1][:self.max_boxes]`; dataset/coco/get_map.py:81-94
+ *           keeps every row = max_boxes 0).
+ *   d_rows f32 [batch, anchors, 6] (tod_nms dets or tod_correct_boxes rows), first d_keep_count[b] valid per image
+ *   max_boxes <= 0: rows keep the NMS output order;  > 0: at most max_boxes rows per image, score descending, ties in kept
+ *                   order (numpy's default argsort is unstable, so the reference defines no tie order)
+ *   d_offsets i32 [batch + 1]: image b's rows are d_packed[d_offsets[b] .. d_offsets[b + 1]); d_offsets[batch] = total
+ *   d_packed f32 [sum, 6] (capacity batch * anchors rows, or batch * max_boxes)
+ *   d_work: tod_pack_workspace_bytes(batch, anchors) bytes (0 unless anchors > 16384 and max_boxes > 0)
+ */
+int64_t tod_pack_workspace_bytes(int32_t batch, int32_t anchors);
+int tod_pack_detections(const float* d_rows, const int32_t* d_keep_count, int32_t batch, int32_t anchors, int32_t max_boxes,
+                        int32_t* d_offsets, float* d_packed, void* d_work, int64_t work_bytes, void* stream);
 
 /*
  * Letterbox preprocessing on the device.

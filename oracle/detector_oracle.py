@@ -238,6 +238,21 @@ def decode_box(head_out: torch.Tensor, input_shape: Tuple[int, int]) -> torch.Te
     return y
 
 
+def decode_box_tuple(dbox: torch.Tensor, cls: torch.Tensor, anchors: torch.Tensor, strides: torch.Tensor,
+                     input_shape: Tuple[int, int]) -> torch.Tensor:
+    """reference DecodeBox.decode_box on the upstream 5-tuple (dbox, cls, origin_cls, anchors, strides),
+    utils/bbox_utils.py:75-82 with dist2bbox :51-57: dbox (B, 4, A) DFL distances, cls (B, nc, A) logits,
+    anchors (2, A), strides (1, A) -> (B, A, 4+nc)."""
+    lt, rb = torch.split(dbox, 2, 1)
+    x1y1 = anchors.unsqueeze(0) - lt
+    x2y2 = anchors.unsqueeze(0) + rb
+    box = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * strides
+    y = torch.cat((box, cls.sigmoid()), 1).permute(0, 2, 1).clone()
+    y[:, :, :4] = y[:, :, :4] / torch.tensor(
+        [input_shape[1], input_shape[0], input_shape[1], input_shape[0]], dtype=y.dtype)
+    return y
+
+
 # ----------------------------------------------------------------------------- NMS
 def nms_greedy(boxes: np.ndarray, scores: np.ndarray, iou_thr: float) -> np.ndarray:
     """torchvision.ops.nms CPU semantics (called at utils/bbox_utils.py:172), restated.

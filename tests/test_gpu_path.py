@@ -133,6 +133,38 @@ def test_decode_box_from_head_bit_exact(golden):
     assert np.array_equal(got.cpu().numpy(), g["decoded"])
 
 
+@pytest.mark.parametrize("case", ["net", "syn"])
+@pytest.mark.parametrize("on_cpu", [False, True])
+def test_decode_box_tuple_form_vs_reference_fixture(golden, case, on_cpu):
+    """DecodeBox.decode_box on the upstream 5-tuple (dbox, cls, origin_cls, anchors, strides), utils/bbox_utils.py:66-82:
+    box columns bit-exact with the reference, scores within 2e-6 (fp32 exp), inputs given on either device."""
+    from transparent_object_detection_b200 import DecodeBox
+    g = golden("decode_tuple.npz")
+    t = lambda k: torch.from_numpy(g[f"{case}_{k}"]) if on_cpu else torch.from_numpy(g[f"{case}_{k}"]).cuda()
+    want = g[f"{case}_decoded"]
+    nc = want.shape[2] - 4
+    db = DecodeBox(nc, tuple(int(v) for v in g[f"{case}_input_shape"]))
+    anchors = t("anchors").t().contiguous().t()            # the reference hands over a transposed VIEW (model/head.py:53)
+    got = db.decode_box((t("dbox"), t("cls"), None, anchors, t("strides")))
+    assert got.is_cuda != on_cpu and tuple(got.shape) == want.shape
+    got = got.cpu().numpy()
+    assert np.array_equal(got[:, :, :4], want[:, :, :4])
+    assert np.abs(got[:, :, 4:] - want[:, :, 4:]).max() <= 2e-6
+    with pytest.raises(ValueError):
+        db.decode_box((t("dbox"), t("cls"), None))
+
+
+def test_decode_box_tuple_equals_head_tensor_form(golden):
+    """decode_box(5-tuple) == decode_box(head tensor) on the same logits -- through the two C-ABI entries."""
+    from transparent_object_detection_b200 import DecodeBox
+    g, gt = golden("net_n_96x128.npz"), golden("decode_tuple.npz")
+    db = DecodeBox(80, (96, 128))
+    a = db.decode_box(tuple(torch.from_numpy(gt[f"net_{k}"]).cuda() if k else None for k in ("dbox", "cls", None, "anchors", "strides")))
+    b = db.decode_box(torch.from_numpy(g["out"]).cuda())
+    assert torch.equal(a[:, :, :4], b[:, :, :4])
+    assert float((a[:, :, 4:] - b[:, :, 4:]).abs().max()) <= 2e-6
+
+
 def test_decode_nc1_ragged_tiles():
     """nc = 1 (the reference's own coco_classes.txt) and level sizes that are not multiples of the CTA tile."""
     from oracle import detector_oracle as O

@@ -177,3 +177,15 @@ def test_c_oracle_matches_numpy_oracle_at_full_size():
     a = nms_c.nms_keep_indices(pred, 80, 0.001, 0.65)
     b = O.nms_keep_indices(pred, 80, 0.001, 0.65)
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 100
+
+
+@pytest.mark.parametrize("case", ["net", "syn"])
+def test_decode_box_tuple_oracle_bit_exact_vs_reference(golden, case):
+    """oracle.decode_box_tuple == the reference's DecodeBox.decode_box on the upstream 5-tuple (utils/bbox_utils.py:66-82),
+    fixture written by oracle/make_golden_tuple.py from the reference's own code."""
+    g = golden("decode_tuple.npz")
+    t = lambda k: torch.from_numpy(g[f"{case}_{k}"])
+    got = O.decode_box_tuple(t("dbox"), t("cls"), t("anchors"), t("strides"), tuple(int(v) for v in g[f"{case}_input_shape"]))
+    want = g[f"{case}_decoded"]
+    assert np.array_equal(got.numpy()[:, :, :4], want[:, :, :4])          # add / sub / mul / div only: bit-exact anywhere
+    assert np.abs(got.numpy()[:, :, 4:] - want[:, :, 4:]).max() <= 1e-6   # sigmoid: the host's vector exp may differ by ulps

@@ -15,7 +15,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import synth                                        # noqa: E402
+from transparent_object_detection_b200 import synth                                        # noqa: E402
 from transparent_object_detection_b200 import BaseModel         # noqa: E402
 from transparent_object_detection_b200._lib import ConvDesc, check   # noqa: E402
 

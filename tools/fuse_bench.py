@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import synth
+from transparent_object_detection_b200 import synth
 from transparent_object_detection_b200 import BaseModel
 from transparent_object_detection_b200._lib import check
 C_, d, m = synth.SCALES["s"]

@@ -4,7 +4,7 @@ import argparse, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import synth
+from transparent_object_detection_b200 import synth
 from transparent_object_detection_b200 import BaseModel
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--conf", type=float, default=0.05)
 ap.add_argument("--iou", type=float, default=0.5); ap.add_argument("--size", type=int, default=640)

@@ -5,7 +5,8 @@ import argparse, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import detector_oracle as O, synth
+from oracle import detector_oracle as O
+from transparent_object_detection_b200 import synth
 from transparent_object_detection_b200 import DecodeBox
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64); ap.add_argument("--anchors", type=int, default=8400)

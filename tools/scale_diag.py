@@ -3,7 +3,8 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import detector_oracle as O, synth
+from oracle import detector_oracle as O
+from transparent_object_detection_b200 import synth
 from transparent_object_detection_b200 import BaseModel
 scale = sys.argv[1]
 B, H, W = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (2, 64, 96)

@@ -18,7 +18,8 @@ SYMBOLS = (
     "tod_debug_set_conv_profile", "tod_stem_conv_nhwc_u8", "tod_conv2d_head_decode",
     "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
     "tod_conv2d_tail1x1_box_decode", "tod_cbam_workspace_floats", "tod_cbam_nhwc_bf16",
-    "tod_softmax_rows_f32_bf16", "tod_attention_fused", "tod_transpose_bf16",
+    "tod_softmax_rows_f32_bf16", "tod_attention_fused", "tod_transpose_bf16", "tod_decode_box_from_tuple",
+    "tod_pack_workspace_bytes", "tod_pack_detections",
 )
 
 
@@ -127,6 +128,12 @@ def lib() -> C.CDLL:
                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tod_decode_box_from_head.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p]
+    L.tod_decode_box_from_tuple.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.tod_pack_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.tod_pack_workspace_bytes.restype = C.c_int64
+    L.tod_pack_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p]
     L.tod_debug_set_conv_profile.argtypes = [C.c_void_p]
     L.tod_resample_coeffs_bicubic.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]

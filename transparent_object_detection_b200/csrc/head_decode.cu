@@ -207,9 +207,64 @@ __global__ void __launch_bounds__(256) decode_box_transpose_kernel(const float* 
   }
 }
 
+// DecodeBox.decode_box on the upstream 5-tuple (utils/bbox_utils.py:66-82): dbox = the DFL distances (B, 4, A) in grid
+// units, cls = class logits (B, nc, A), anchors (2, A), strides (A):
+//   dist2bbox(dbox, anchors, xywh, dim 1) * strides  |  sigmoid(cls)  ->  permute(0, 2, 1)  ->  xywh / (W, H, W, H)
+// in the reference's float32 operation order (this file is compiled with -fmad=false).  One CTA = 32 anchors of one
+// image: channel rows are read along A (coalesced), staged in shared memory and written as 32 contiguous output rows.
+__global__ void __launch_bounds__(256) decode_tuple_kernel(const float* __restrict__ dbox, const float* __restrict__ cls,
+                                                           const float* __restrict__ anchor_xy, const float* __restrict__ strides,
+                                                           float* __restrict__ out, int nc, int anchors, float in_w, float in_h) {
+  extern __shared__ float rows[];          // [32][no]
+  const int no = 4 + nc;
+  const int b = blockIdx.y, a0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 anchors x 8 channel lanes
+  const int a = a0 + tx;
+  if (a < anchors) {
+    if (ty == 0) {
+      const float* d = dbox + static_cast<size_t>(b) * 4 * anchors + a;
+      const float ax = anchor_xy[a], ay = anchor_xy[anchors + a], st = strides[a];
+      const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[anchors]);                       // anchors - lt
+      const float x2 = __fadd_rn(ax, d[2 * static_cast<size_t>(anchors)]), y2 = __fadd_rn(ay, d[3 * static_cast<size_t>(anchors)]);
+      float* r = rows + tx * no;
+      r[0] = __fdiv_rn(__fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.0f), st), in_w);                // ((x1y1 + x2y2) / 2) * s / W
+      r[1] = __fdiv_rn(__fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.0f), st), in_h);
+      r[2] = __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), st), in_w);
+      r[3] = __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), st), in_h);
+    }
+    const float* c = cls + static_cast<size_t>(b) * nc * anchors + a;
+    for (int ch = ty; ch < nc; ch += 8) rows[tx * no + 4 + ch] = sigmoid_ref(c[static_cast<size_t>(ch) * anchors]);
+  }
+  __syncthreads();
+  const int n_valid = min(32, anchors - a0) * no;
+  float* dst = out + (static_cast<size_t>(b) * anchors + a0) * no;
+  for (int i = threadIdx.x; i < n_valid; i += 256) dst[i] = rows[i];
+}
+
 }  // namespace tod
 
 using namespace tod;
+
+extern "C" int tod_decode_box_from_tuple(const float* d_dbox, const float* d_cls, const float* d_anchors, const float* d_strides,
+                                         float* d_decoded, int32_t batch, int32_t nc, int32_t anchors, int32_t in_h,
+                                         int32_t in_w, void* stream) {
+  TOD_CHECK_ARG(d_dbox && d_cls && d_anchors && d_strides && d_decoded, "decode_box(tuple): null pointer");
+  TOD_CHECK_ARG(batch > 0 && batch <= 65535 && nc > 0 && nc <= 4096 && anchors > 0 && in_h > 0 && in_w > 0,
+                "decode_box(tuple): bad shape");
+  const size_t smem = static_cast<size_t>(32) * (4 + nc) * sizeof(float);
+  static PerDeviceOnce attr_once;
+  if (attr_once.needed()) {
+    int rc = check_cuda(cudaFuncSetAttribute(decode_tuple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                        "cudaFuncSetAttribute(decode_tuple)");
+    if (rc != TOD_OK) return rc;
+    attr_once.done();
+  }
+  TOD_CHECK_ARG(smem <= 200 * 1024, "decode_box(tuple): nc %d too large for shared memory", nc);
+  decode_tuple_kernel<<<dim3(ceil_div(anchors, 32), batch), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_dbox, d_cls, d_anchors, d_strides, d_decoded, nc, anchors, static_cast<float>(in_w), static_cast<float>(in_h));
+  TOD_CHECK_LAUNCH("decode_tuple_kernel launch");
+  return TOD_OK;
+}
 
 extern "C" int tod_head_decode(const tod_decode_desc* d, void* stream) {
   TOD_CHECK_ARG(d != nullptr, "decode: null descriptor");

@@ -468,6 +468,68 @@ __global__ void __launch_bounds__(256) nms_compact_kernel(const float4* __restri
   if (threadIdx.x == 0) keep_count[b] = s_base;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Result packing: the kept rows of a batch, compacted image after image, so that ONE small
+// device-to-host copy carries every detection -- and, with max_boxes > 0, the top-`max_boxes` selection of the reference's
+// detect loop, utils/callbacks.py:159-166 (`top_100 = np.argsort(top_conf)[::-1][:self.max_boxes]`).  Tie order is defined
+// here as score descending, then kept order (the reference's numpy argsort is an unstable sort and defines none).
+// One CTA per image: offset = sum of the earlier images' output counts; keys (~score | row) bitonic-sorted in shared
+// memory (global workspace beyond kSortSmemKeys rows).
+__global__ void __launch_bounds__(kSortThreads) pack_detections_kernel(const float* __restrict__ rows, const int* __restrict__ keep_count,
+                                                                       int anchors, int max_boxes, int* __restrict__ offsets,
+                                                                       float* __restrict__ out, unsigned long long* __restrict__ keys_g,
+                                                                       int a_pow2) {
+  extern __shared__ unsigned long long sort_smem[];
+  __shared__ int s_part[kSortThreads / 32];
+  __shared__ int s_off;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = keep_count[b];
+  const int k = max_boxes > 0 ? min(n, max_boxes) : n;
+  int part = 0;
+  for (int i = threadIdx.x; i < b; i += kSortThreads) part += max_boxes > 0 ? min(keep_count[i], max_boxes) : keep_count[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int w = 0; w < kSortThreads / 32; ++w) off += s_part[w];
+    s_off = off;
+    offsets[b] = off;
+    if (b == static_cast<int>(gridDim.x) - 1) offsets[b + 1] = off + k;
+  }
+  __syncthreads();
+  const float* src = rows + static_cast<size_t>(b) * anchors * 6;
+  float* dst = out + static_cast<size_t>(s_off) * 6;
+  if (max_boxes <= 0) {                       // plain compaction in the NMS output order
+    for (int i = threadIdx.x; i < n * 6; i += kSortThreads) dst[i] = src[i];
+    return;
+  }
+  unsigned long long* keys = keys_g ? keys_g + static_cast<size_t>(b) * a_pow2 : sort_smem;
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  for (int i = threadIdx.x; i < n_pad; i += kSortThreads)
+    keys[i] = i < n ? (static_cast<unsigned long long>(score_desc_bits(src[i * 6 + 4])) << 32) | static_cast<unsigned>(i) : ~0ull;
+  __syncthreads();
+  for (int kk = 2; kk <= n_pad; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n_pad >> 1); t += kSortThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = keys[i], c = keys[l];
+        const bool up = (i & kk) == 0;
+        if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k * 6; i += kSortThreads) {
+    const int r = i / 6, c = i - r * 6;
+    dst[i] = src[static_cast<size_t>(keys[r] & 0xffffffffull) * 6 + c];
+  }
+}
+
 }  // namespace tod
 
 using namespace tod;
@@ -536,5 +598,35 @@ extern "C" int tod_correct_boxes(const float* d_dets, const int32_t* d_keep_coun
   correct_boxes_kernel<<<dim3(4, batch), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dets, d_keep_count, anchors, d_params,
                                                                                       letterbox, d_rows);
   TOD_CHECK_LAUNCH("correct_boxes_kernel launch");
+  return TOD_OK;
+}
+
+extern "C" int64_t tod_pack_workspace_bytes(int32_t batch, int32_t anchors) {
+  if (batch <= 0 || anchors <= 0) return 0;
+  const int ap2 = next_pow2(anchors);
+  return ap2 > kSortSmemKeys ? static_cast<int64_t>(batch) * ap2 * 8 : 0;
+}
+
+extern "C" int tod_pack_detections(const float* d_rows, const int32_t* d_keep_count, int32_t batch, int32_t anchors,
+                                   int32_t max_boxes, int32_t* d_offsets, float* d_packed, void* d_work, int64_t work_bytes,
+                                   void* stream) {
+  TOD_CHECK_ARG(d_rows && d_keep_count && d_offsets && d_packed, "pack_detections: null pointer");
+  TOD_CHECK_ARG(batch > 0 && batch <= 65535 && anchors > 0, "pack_detections: bad sizes");
+  const int ap2 = next_pow2(anchors);
+  const int64_t need = max_boxes > 0 ? tod_pack_workspace_bytes(batch, anchors) : 0;
+  TOD_CHECK_ARG(need == 0 || (d_work != nullptr && work_bytes >= need && (reinterpret_cast<uintptr_t>(d_work) & 7) == 0),
+                "pack_detections: workspace %lld < %lld bytes", (long long)work_bytes, (long long)need);
+  static PerDeviceOnce attr_once;
+  if (attr_once.needed()) {
+    int rc = check_cuda(cudaFuncSetAttribute(pack_detections_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8),
+                        "cudaFuncSetAttribute(pack_detections)");
+    if (rc != TOD_OK) return rc;
+    attr_once.done();
+  }
+  const size_t smem = (max_boxes > 0 && need == 0) ? static_cast<size_t>(ap2) * 8 : 0;
+  pack_detections_kernel<<<batch, kSortThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_rows, d_keep_count, anchors, max_boxes, d_offsets, d_packed,
+      need ? reinterpret_cast<unsigned long long*>(d_work) : nullptr, ap2);
+  TOD_CHECK_LAUNCH("pack_detections_kernel launch");
   return TOD_OK;
 }

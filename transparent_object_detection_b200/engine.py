@@ -111,11 +111,10 @@ class DetectorEngine:
         self.launches_forward = 0
         self.fork_head = True          # head towers as parallel graph branches (graph_for)
         self.prioritise_critical_path = os.environ.get("TOD_GRAPH_PRIO", "1") != "0"
-        self._graph = None
         self._box_params = None
         self._graphs: Dict[Tuple, "torch.cuda.CUDAGraph"] = {}   # (input kind, slot, conf, iou, head_out, decoded)
         self._inputs: Dict[Tuple[str, int], torch.Tensor] = {}   # static input buffers per (kind, slot)
-        self._slot_out: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._packed: Optional[dict] = None
         self._side_streams: Dict[Tuple[str, int], "torch.cuda.Stream"] = {}
         self._build(state_dict)
 
@@ -457,11 +456,23 @@ class DetectorEngine:
             self._inputs[key] = torch.zeros(shape, dtype=torch.float32 if kind == "f32" else torch.uint8, device=self.device)
         return self._inputs[key]
 
-    def slot_outputs(self, slot: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Per-slot copies of (keep_count, dets): the graph's own result buffers are reused by the next replay."""
-        if slot not in self._slot_out:
-            self._slot_out[slot] = (torch.zeros_like(self.keep_count), torch.zeros_like(self.dets))
-        return self._slot_out[slot]
+    def packed_buffers(self) -> dict:
+        """Result buffers of the captured graphs (tod_pack_detections): ONE device buffer = int32 offsets[B + 1] (padded to
+        `hdr` bytes) followed by the compacted rows, and its pinned host mirror, which the graph itself fills with a single
+        fixed-size device-to-host copy of the header and the first `cap_rows` rows (collect() fetches the rest only when a
+        batch holds more)."""
+        if self._packed is None:
+            B, A = self.batch, self.anchors
+            hdr = (4 * (B + 1) + 31) // 32 * 32
+            cap_rows = min(B * A, max(B * 256, 4096))
+            dev = torch.zeros(hdr + B * A * 24, dtype=torch.uint8, device=self.device)
+            host = torch.zeros(hdr + cap_rows * 24, dtype=torch.uint8).pin_memory()
+            work = torch.zeros(max(int(self.L.tod_pack_workspace_bytes(B, A)), 8), dtype=torch.uint8, device=self.device)
+            self._packed = dict(dev=dev, host=host, hdr=hdr, cap_rows=cap_rows, work=work,
+                                rows_corrected=torch.zeros((B, A, 6), dtype=torch.float32, device=self.device),
+                                host_offsets=host[:4 * (B + 1)].view(torch.int32).numpy(),
+                                host_rows=host[hdr:].view(torch.float32).view(cap_rows, 6).numpy())
+        return self._packed
 
     def run_network(self, x: Optional[torch.Tensor] = None, fork: bool = False, fused_decode: bool = False) -> None:
         """Enqueue stem + every conv + SPPF pooling (the raw head maps land in self.raw).
@@ -572,29 +583,7 @@ class DetectorEngine:
         extra = sum(4 if k == "cbam" else ((4 if p["fused"] else 6 * self.batch - 1) if k == "attn" else 0)
                     for k, _, p in self.ops)
         return (len(self.ops) + extra - len(self.tail_skip) - (len(self.tail_box_skip) if self.fuse_head_decode else 0)
-                + (0 if self.fuse_head_decode else 1) + 3)
-
-    def capture(self, conf_thres: float, nms_thres: float, head_out: bool = False, decoded: bool = False) -> None:
-        """Capture network + decode + NMS on the static input into one CUDA graph."""
-        s = torch.cuda.Stream(self.device)
-        s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s):
-            for _ in range(2):  # warm-up outside capture (sets function attributes, loads modules)
-                self.run_network()
-                self.run_decode(head_out, decoded, True)
-                self.run_nms(conf_thres, nms_thres)
-        torch.cuda.current_stream(self.device).wait_stream(s)
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.run_network()
-            self.run_decode(head_out, decoded, True)
-            self.run_nms(conf_thres, nms_thres)
-        self._graph = g
-        self._graph_key = (float(conf_thres), float(nms_thres), head_out, decoded)
-
-    def replay(self) -> None:
-        self._graph.replay()
+                + (0 if self.fuse_head_decode else 1) + 3 + 1)      # ... + 3 NMS kernels + result packing
 
     def box_params(self) -> torch.Tensor:
         """(B, 6) float64 device buffer read by tod_correct_boxes in the `corrected` graphs: per image
@@ -604,29 +593,39 @@ class DetectorEngine:
             self._box_params[:, 2:4] = 1.0
         return self._box_params
 
-    def graph_for(self, kind: str, slot: int, conf_thres: float, nms_thres: float, corrected: int = -1):
-        """CUDA graph of network + decode + NMS (+ the results into the slot's buffers) on the static input
-        (kind, slot); captured on first use.  corrected = 0 / 1: the slot's rows are un-letterboxed on the device
-        (tod_correct_boxes with letterbox off / on, parameters in box_params()); -1: raw NMS rows [x1, y1, x2, y2, ..]."""
-        key = (kind, slot, float(conf_thres), float(nms_thres), int(corrected))
+    def run_pack(self, corrected: int = -1, max_boxes: int = 0) -> None:
+        """NMS rows -> (un-letterboxed rows) -> packed result buffer -> pinned host mirror (one fixed-size D2H copy).
+        corrected = 0 / 1: tod_correct_boxes with letterbox off / on (parameters in box_params()); -1: raw NMS rows."""
+        pk = self.packed_buffers()
+        rows = self.dets
+        if corrected >= 0:
+            rows = pk["rows_corrected"]
+            check(self.L.tod_correct_boxes(self.dets.data_ptr(), self.keep_count.data_ptr(), self.batch, self.anchors,
+                                           self.box_params().data_ptr(), int(corrected), rows.data_ptr(), self._stream()),
+                  "tod_correct_boxes")
+        dev = pk["dev"]
+        check(self.L.tod_pack_detections(rows.data_ptr(), self.keep_count.data_ptr(), self.batch, self.anchors, int(max_boxes),
+                                         dev.data_ptr(), dev.data_ptr() + pk["hdr"], pk["work"].data_ptr(), pk["work"].numel(),
+                                         self._stream()), "tod_pack_detections")
+        pk["host"].copy_(dev[:pk["host"].numel()], non_blocking=True)
+
+    def graph_for(self, kind: str, slot: int, conf_thres: float, nms_thres: float, corrected: int = -1, max_boxes: int = 0):
+        """CUDA graph of network + decode + NMS + result packing (+ the D2H copy of the packed rows into the pinned host
+        mirror) on the static input (kind, slot); captured on first use.  corrected = 0 / 1: rows un-letterboxed on the
+        device; max_boxes > 0: the reference detect loop's top-k (utils/callbacks.py:159-166) on the device."""
+        key = (kind, slot, float(conf_thres), float(nms_thres), int(corrected), int(max_boxes))
         g = self._graphs.get(key)
         if g is not None:
             return g
         x = self.input_buffer(kind, slot)
-        cnt, dets = self.slot_outputs(slot)
+        self.packed_buffers()
 
         def body():
             self.run_network(x, fork=self.fork_head, fused_decode=self.fuse_head_decode)
             if not self.fuse_head_decode:
                 self.run_decode(False, False, True)
             self.run_nms(conf_thres, nms_thres)
-            cnt.copy_(self.keep_count)
-            if corrected >= 0:
-                check(self.L.tod_correct_boxes(self.dets.data_ptr(), self.keep_count.data_ptr(), self.batch, self.anchors,
-                                               self.box_params().data_ptr(), int(corrected), dets.data_ptr(), self._stream()),
-                      "tod_correct_boxes")
-            else:
-                dets.copy_(self.dets)
+            self.run_pack(corrected, max_boxes)
 
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))

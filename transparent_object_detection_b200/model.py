@@ -189,11 +189,32 @@ class DecodeBox:
         self.input_shape = input_shape
 
     def decode_box(self, inputs) -> torch.Tensor:
-        """utils/bbox_utils.py:66-82.  Accepts the Head eval tensor (B, 4+nc, A) the reference's own head
-        returns -> (B, A, 4+nc) with xywh normalised by (W, H, W, H)."""
+        """utils/bbox_utils.py:66-82.  Accepts BOTH forms the reference's code base uses:
+          * the upstream 5-tuple (dbox, cls, origin_cls, anchors, strides) its callers pass (utils/callbacks.py:150-151,
+            dataset/coco/get_map.py:68-69): dbox (B, 4, A) DFL distances, cls (B, nc, A) logits, anchors (2, A),
+            strides (1, A) -> tod_decode_box_from_tuple;
+          * the Head eval tensor (B, 4+nc, A) the reference's own head returns -> tod_decode_box_from_head.
+        Both give (B, A, 4+nc) with xywh normalised by (W, H, W, H)."""
         if isinstance(inputs, (tuple, list)):
-            raise NotImplementedError("decode_box: pass the (B, 4+nc, A) head tensor (the reference head's eval output); "
-                                      "the upstream 5-tuple form is not produced by this model")
+            if len(inputs) != 5:
+                raise ValueError("decode_box expects (dbox, cls, origin_cls, anchors, strides) or the (B, 4+nc, A) head tensor")
+            dbox, cls, _origin_cls, anchors, strides = inputs
+            if dbox.dim() != 3 or dbox.shape[1] != 4 or cls.dim() != 3 or cls.shape[0] != dbox.shape[0] or cls.shape[2] != dbox.shape[2]:
+                raise ValueError(f"decode_box: dbox {tuple(dbox.shape)} / cls {tuple(cls.shape)} are not (B, 4, A) / (B, nc, A)")
+            B, nc, A = cls.shape
+            if anchors.numel() != 2 * A or strides.numel() != A:
+                raise ValueError(f"decode_box: anchors {tuple(anchors.shape)} / strides {tuple(strides.shape)} do not match A = {A}")
+            was_cpu = not dbox.is_cuda
+            dev = dbox.device if dbox.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+            dbox, cls, anchors, strides = f32(dbox), f32(cls), f32(anchors.reshape(2, A)), f32(strides.reshape(A))
+            out = torch.empty((B, A, 4 + nc), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                check(_lib.lib().tod_decode_box_from_tuple(dbox.data_ptr(), cls.data_ptr(), anchors.data_ptr(), strides.data_ptr(),
+                                                           out.data_ptr(), B, nc, A, int(self.input_shape[0]),
+                                                           int(self.input_shape[1]), torch.cuda.current_stream().cuda_stream),
+                      "tod_decode_box_from_tuple")
+            return out.cpu() if was_cpu else out
         y = inputs
         if y.dim() != 3 or y.shape[1] != self.bbox_attrs:
             raise ValueError(f"decode_box expects (B, {self.bbox_attrs}, A), got {tuple(y.shape)}")
@@ -327,43 +348,29 @@ class Detector:
         self.confidence, self.nms_iou, self.letterbox_image, self.max_boxes = confidence, nms_iou, letterbox_image, max_boxes
         self.bbox_util = DecodeBox(model.num_classes, self.input_shape)
 
-    def _engine(self, batch: int, device) -> DetectorEngine:
-        eng = self.model.engine(batch, self.input_shape[0], self.input_shape[1], device)
-        key = (float(self.confidence), float(self.nms_iou), False, False)
-        if eng._graph is None or eng._graph_key != key:
-            with torch.cuda.device(eng.device):
-                eng.capture(self.confidence, self.nms_iou)
-        return eng
-
-    def detect_device(self, images: torch.Tensor):
-        """images: float32 (B, 3, H, W), host (pinned preferred) or device.  Returns the engine whose
-        keep_count / keep_idx / dets buffers hold the result (no host sync)."""
-        dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        eng = self._engine(images.shape[0], dev)
-        eng.x_static.copy_(images, non_blocking=True)
-        eng.replay()
-        return eng
-
-    def detect(self, images: torch.Tensor, image_shape=None) -> List[Optional[np.ndarray]]:
+    def detect(self, images: torch.Tensor, image_shape=None, max_boxes: int = 0) -> List[Optional[np.ndarray]]:
         """-> list of None | float32 (n, 6) rows [y1, x1, y2, x2, conf, cls] like non_max_suppression.
-        images: float32 (B, 3, H, W) in [0, 1] (the reference's tensor) or uint8 (B, H, W, 3) letterboxed RGB."""
-        return self.collect(self.submit(images, image_shape if image_shape is not None else self.input_shape))
+        images: float32 (B, 3, H, W) in [0, 1] (the reference's tensor) or uint8 (B, H, W, 3) letterboxed RGB.
+        max_boxes > 0: at most that many rows per image, score descending (the top-k of utils/callbacks.py:159-166)."""
+        return self.collect(self.submit(images, image_shape if image_shape is not None else self.input_shape, max_boxes))
 
     # -- pipelined form: submit batch i+1 before collecting batch i and the upload overlaps the previous replay ---------
-    def submit(self, images: torch.Tensor, image_shape=None) -> "PendingBatch":
-        """Enqueue upload (copy stream) -> graph replay (compute stream) of one batch and return at once.
+    def submit(self, images: torch.Tensor, image_shape=None, max_boxes: int = 0) -> "PendingBatch":
+        """Enqueue upload (copy stream) -> graph replay (compute stream) of one batch and return at once.  Up to
+        `pipeline_depth` batches may be in flight; submitting one more first collects the oldest into its handle.
         image_shape: (h, w) of the original images, or one (h, w) per image; when given, the kept rows are un-letterboxed
         on the device (tod_correct_boxes) and collect() only slices them; otherwise collect(pending, image_shape) does
-        it on the host like the reference (utils/bbox_utils.py:176-180)."""
+        it on the host like the reference (utils/bbox_utils.py:176-180).
+        max_boxes > 0: top-k on the device (tod_pack_detections)."""
         if images.dim() != 4 or images.dtype not in (torch.float32, torch.uint8):
             raise ValueError("images must be float32 (B, 3, H, W) or uint8 (B, H, W, 3)")
         kind = "u8" if images.dtype == torch.uint8 else "f32"
         if (kind == "u8" and images.shape[3] != 3) or (kind == "f32" and images.shape[1] != 3):
             raise ValueError(f"bad image batch shape {tuple(images.shape)} for dtype {images.dtype}")
         dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        return self._submit(images.shape[0], dev, kind, lambda x: x.copy_(images, non_blocking=True), image_shape)
+        return self._submit(images.shape[0], dev, kind, lambda x: x.copy_(images, non_blocking=True), image_shape, max_boxes)
 
-    def submit_images(self, images: Sequence, device=None) -> "PendingBatch":
+    def submit_images(self, images: Sequence, device=None, max_boxes: int = 0) -> "PendingBatch":
         """Raw RGB images of any sizes ((h, w, 3) uint8 arrays / tensors or PIL images) -> letterbox ON THE DEVICE
         (csrc/letterbox.cu, bit-exact with the reference's Pillow BICUBIC resize_image, utils/utils.py:16-30) straight
         into the network's uint8 input batch -> the same graph replay as submit().  collect() un-letterboxes every
@@ -396,10 +403,11 @@ class Detector:
                 self._letterbox(src, x[i:j])
                 i = j
 
-        return self._submit(len(arrs), dev, "u8", fill, np.array([[a.shape[0], a.shape[1]] for a in arrs]))
+        return self._submit(len(arrs), dev, "u8", fill, np.array([[a.shape[0], a.shape[1]] for a in arrs]), max_boxes)
 
-    def _submit(self, batch: int, dev, kind: str, fill, image_shapes=None) -> "PendingBatch":
-        """One pipeline step: `fill(x)` populates the plan's static input x on the copy stream, then the graph replays."""
+    def _submit(self, batch: int, dev, kind: str, fill, image_shapes=None, max_boxes: int = 0) -> "PendingBatch":
+        """One pipeline step: `fill(x)` populates the plan's static input x on the copy stream, then the graph replays
+        (network + decode + NMS + un-letterbox + packing + the D2H copy of the packed rows into pinned host memory)."""
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         if not hasattr(self, "_pipe"):
@@ -409,18 +417,29 @@ class Detector:
         if st is None:
             with torch.cuda.device(dev):
                 st = {"copy": torch.cuda.Stream(dev), "compute": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)], "seq": 0,
-                      "free": [None] * self.pipeline_depth}
+                      "free": [None] * self.pipeline_depth, "pending": [None] * self.pipeline_depth, "graph_keys": set()}
             self._pipe[pkey] = st
         seq = st["seq"]
         st["seq"] = seq + 1
         slot = seq % self.pipeline_depth
+        # the plan (arena, graph, result buffers) of this slot is reused: a batch still held by the caller is collected
+        # into its handle first, so that an old handle can never return a newer batch's rows
+        prev = st["pending"][slot]
+        if prev is not None and prev.result is None:
+            prev.result = self._fetch(prev, None)
         # `pipeline_depth` independent plans (own activation arena, graph, result buffers) over two compute streams that
         # consecutive batches alternate on: the tail of batch i (NMS: a few CTAs) and the first layers of batch i+1 overlap
         # instead of serialising, while batch i+2 uploads.  A plan is reused only after its previous batch has finished.
         eng = self.model.engine(batch, self.input_shape[0], self.input_shape[1], dev, instance=slot)
         with torch.cuda.device(eng.device):
             corrected = -1 if image_shapes is None else int(bool(self.letterbox_image))
-            g = eng.graph_for(kind, 0, self.confidence, self.nms_iou, corrected)       # captured on first use
+            gkey = (slot, kind, float(self.confidence), float(self.nms_iou), corrected, int(max_boxes))
+            if gkey not in st["graph_keys"]:
+                # first use of these thresholds on this plan: graph_for runs an eager warm-up pass on the plan's arena,
+                # which must not race a batch still in flight on it
+                torch.cuda.synchronize(eng.device)
+                st["graph_keys"].add(gkey)
+            g = eng.graph_for(kind, 0, self.confidence, self.nms_iou, corrected, max_boxes)       # captured on first use
             x = eng.input_buffer(kind, 0)
             caller = torch.cuda.current_stream(eng.device)
             compute = st["compute"][seq & 1]
@@ -442,36 +461,63 @@ class Detector:
             st["free"][slot] = done
         pend = PendingBatch(eng, 0, done)
         pend.corrected = image_shapes is not None
+        st["pending"][slot] = pend
         return pend
 
-    def collect(self, pending: "PendingBatch", image_shape=None) -> List[Optional[np.ndarray]]:
-        """Wait for a submitted batch and return the reference's rows (D2H of the counts, then of the kept rows only)."""
+    def _fetch(self, pending: "PendingBatch", image_shape) -> List[Optional[np.ndarray]]:
         eng = pending.engine
-        pending.done.synchronize()
-        cnt, dets = eng.slot_outputs(pending.slot)
-        counts = cnt.cpu().numpy()
-        if pending.corrected:                  # rows were un-letterboxed on the device: slice only
-            if image_shape is not None:
-                raise ValueError("this batch was submitted with its image shapes; collect() takes none")
-            rows: List[Optional[np.ndarray]] = [None] * len(counts)
-            mx = int(counts.max()) if len(counts) else 0
-            if mx > 0:
-                host = dets[:, :mx].cpu().numpy()
-                for i, n in enumerate(counts):
-                    if n > 0:
-                        rows[i] = host[i, :n].copy()
-        else:
-            shape = image_shape if image_shape is not None else self.input_shape
-            rows = dets_to_reference_rows(dets, counts, self.input_shape, shape, self.letterbox_image)
-        pending.d2h_bytes = counts.nbytes + int(counts.max() if len(counts) else 0) * counts.shape[0] * 24
-        return rows
+        pending.done.synchronize()                               # the graph's own D2H copy has landed in pinned memory
+        pk = eng.packed_buffers()
+        B = eng.batch
+        off = pk["host_offsets"].copy()
+        total = int(off[B])
+        pending.d2h_bytes = int(pk["host"].numel())
+        if total <= pk["cap_rows"]:
+            packed = pk["host_rows"][:total].copy()              # (the pinned mirror is overwritten by the plan's next batch)
+        else:                                                    # rare: more rows than the fixed-size copy carries
+            with torch.cuda.device(eng.device):
+                packed = pk["dev"][pk["hdr"]:pk["hdr"] + total * 24].view(torch.float32).view(total, 6).cpu().numpy()
+            pending.d2h_bytes += (total - pk["cap_rows"]) * 24
+        if not pending.corrected and total > 0:                  # un-letterbox on the host like the reference (:176-180)
+            shape = np.asarray(image_shape if image_shape is not None else self.input_shape)
+            box_xy, box_wh = (packed[:, 0:2] + packed[:, 2:4]) / 2, packed[:, 2:4] - packed[:, 0:2]
+            if shape.ndim == 2:                                  # one (h, w) per image: the letterbox geometry differs
+                if shape.shape[0] != B:
+                    raise ValueError(f"{shape.shape[0]} image shapes for {B} images")
+                for i in range(B):
+                    a, b = off[i], off[i + 1]
+                    if b > a:
+                        packed[a:b, :4] = DecodeBox.correct_boxes(box_xy[a:b], box_wh[a:b], self.input_shape, shape[i], self.letterbox_image)
+            else:
+                packed[:, :4] = DecodeBox.correct_boxes(box_xy, box_wh, self.input_shape, shape, self.letterbox_image)
+        return [packed[off[i]:off[i + 1]] if off[i + 1] > off[i] else None for i in range(B)]
+
+    def collect(self, pending: "PendingBatch", image_shape=None) -> List[Optional[np.ndarray]]:
+        """Wait for a submitted batch and return the reference's rows: the graph has already copied the packed rows to
+        pinned host memory, so this is an event wait plus slicing (per-image views of one array)."""
+        if pending.corrected and image_shape is not None:
+            raise ValueError("this batch was submitted with its image shapes; collect() takes none")
+        if pending.result is None:
+            pending.result = self._fetch(pending, image_shape)
+        return pending.result
 
     def top_boxes(self, rows: Optional[np.ndarray]) -> Optional[np.ndarray]:
-        """The `max_boxes` highest-scoring rows in the reference's order (utils/callbacks.py:163-166:
-        `np.argsort(top_conf)[::-1][:self.max_boxes]` -- the same numpy call, hence the same tie order)."""
+        """The `max_boxes` highest-scoring rows with the reference's own host expression (utils/callbacks.py:163-166:
+        `np.argsort(top_conf)[::-1][:self.max_boxes]`).  numpy's default argsort is unstable, so rows of EQUAL score come
+        out in an order the reference does not define; the device path (max_boxes= of detect / submit, or detect_top)
+        defines it as score descending, then kept order."""
         if rows is None:
             return None
         return rows[np.argsort(rows[:, 4])[::-1][:self.max_boxes]]
+
+    def detect_top(self, images: torch.Tensor, image_shape=None):
+        """The reference detect loop's result variables (utils/callbacks.py:156-166) per image, selected ON THE DEVICE:
+        -> list of None | (top_label int32 (k,), top_conf float32 (k,), top_boxes float32 (k, 4) [top, left, bottom, right]),
+        k <= self.max_boxes, score descending."""
+        out = []
+        for rows in self.detect(images, image_shape, max_boxes=self.max_boxes):
+            out.append(None if rows is None else (np.array(rows[:, 5], dtype="int32"), rows[:, 4], rows[:, :4]))
+        return out
 
     def detect_image_rows(self, image) -> Optional[np.ndarray]:
         """One PIL image / (H, W, 3) uint8 array -> the reference's (n, 6) rows or None.  The raw pixels go to the GPU as
@@ -521,6 +567,7 @@ class PendingBatch:
     def __init__(self, engine: DetectorEngine, slot: int, done: "torch.cuda.Event"):
         self.engine, self.slot, self.done, self.d2h_bytes = engine, slot, done, 0
         self.corrected = False            # rows already un-letterboxed on the device (submit got the image shapes)
+        self.result = None                # the rows, once fetched (collect() is idempotent)
 
 
 def _letterbox(image, size, letterbox_image):
