@@ -198,3 +198,29 @@ def test_self_attention_other_widths_against_oracle(c, h, w):
     with torch.no_grad():
         ref = O.self_attention({"m." + k: v for k, v in sd.items()}, "m", x.to(torch.bfloat16).float())
     assert float(((y - ref).abs() > 6e-2 * ref.abs() + 6e-2).float().mean()) <= 2e-3, float((y - ref).abs().max())
+
+
+def test_unfused_self_attention_changing_inputs_with_poisoned_temporaries():
+    """in the unfused chain the "weight" operand of the scores / value^T / output GEMMs is an activation the
+    previous kernel has just written (TOD_CONV_DYNAMIC_W).  A kernel that prefetched it ahead of its programmatic-launch
+    wait would read the PREVIOUS call's (or poisoned) memory: two different inputs back to back, the allocator's free
+    blocks filled with NaN in between, each result checked against the emulation of ITS input."""
+    from transparent_object_detection_b200.attention import SelfAttention
+    g = torch.Generator().manual_seed(21)
+    c, h, w = 64, 16, 24              # q / k width 8 -> padded to 16, cout = N = 384 > 128: the resident-weight plan
+    m = SelfAttention(c)
+    m.fused = False
+    sd = {"query.weight": torch.randn((c // 8, c, 1, 1), generator=g) * 0.1, "query.bias": torch.randn((c // 8,), generator=g) * 0.1,
+          "key.weight": torch.randn((c // 8, c, 1, 1), generator=g) * 0.1, "key.bias": torch.randn((c // 8,), generator=g) * 0.1,
+          "value.weight": torch.randn((c, c, 1, 1), generator=g) * 0.1, "value.bias": torch.randn((c,), generator=g) * 0.1,
+          "gamma": torch.tensor([0.7])}
+    m.load_state_dict(sd)
+    for it in range(4):
+        x = torch.randn((2, c, h, w), generator=g) * (1.0 + it)
+        junk = [torch.full((n,), float("nan"), dtype=torch.float32, device="cuda") for n in (1 << 12, 1 << 16, 1 << 20, 1 << 22)]
+        torch.cuda.synchronize()
+        del junk                                      # freed blocks keep their NaN contents and are handed out again
+        y = m(x.cuda()).cpu()
+        emu = _sa_bf16_emulation(sd, x, False)
+        assert torch.isfinite(y).all(), it
+        assert float(((y - emu).abs() > 2e-2 * emu.abs() + 2e-2).float().mean()) == 0.0, (it, float((y - emu).abs().max()))
