@@ -1,9 +1,9 @@
 """GPU parity of the non-GEMM kernels and of the whole path (through the C ABI / drop-in classes) against the
 CPU oracle (oracle/detector_oracle.py) and the reference-generated fixtures in tests/golden/.
 
-Stated tolerances (SURVEY.md section 8c, bf16 activations with fp32 accumulation):
-  stage features : max-abs error <= 3 % of the reference abs-max, RMS-relative <= 1.5 %
-  decoded boxes  : <= 1.5 px at 640 input;  scores <= 8e-3
+Stated tolerances (SURVEY.md section 8c, bf16 activations with fp32 accumulation; scales n and s):
+  stage features : max-abs error <= 2 % of the reference abs-max, RMS-relative <= 1 %
+  decoded boxes  : <= 1 px;  scores <= 5e-3
   decode kernel on fp32 raw maps: boxes <= 2e-3 px, scores <= 2e-6 (fp32 exp differences only)
   NMS            : keep indices / rows bit-exact when fed the oracle's (reference's) decoded tensor
 """
@@ -326,14 +326,16 @@ def test_network_scale_n_matches_reference_fixture(golden):
     torch.cuda.synchronize()
     for name in ("p3", "p4", "p5", "h2", "h4", "h6"):
         mx, rms = _rel_stats(eng.feature_nchw(name).cpu().numpy(), g[name])
-        assert mx <= 0.03 and rms <= 0.015, (name, mx, rms)
+        print(f"scale n {name}: max-abs err / abs-max {mx:.4f}, RMS-rel {rms:.4f}")
+        assert mx <= 0.02 and rms <= 0.01, (name, mx, rms)
     raw = [r.float().cpu().numpy() for r in eng.raw_maps_nchw()]
     for i in range(3):
         assert np.abs(raw[i] - g[f"raw{i}"]).max() <= 0.08, (i, np.abs(raw[i] - g[f"raw{i}"]).max())
     o = out.cpu().numpy()
     assert o.shape == g["out"].shape
-    assert np.abs(o[:, :4] - g["out"][:, :4]).max() <= 1.5, np.abs(o[:, :4] - g["out"][:, :4]).max()
-    assert np.abs(o[:, 4:] - g["out"][:, 4:]).max() <= 8e-3
+    print(f"scale n out: box err {np.abs(o[:, :4] - g['out'][:, :4]).max():.4f} px, score err {np.abs(o[:, 4:] - g['out'][:, 4:]).max():.2e}")
+    assert np.abs(o[:, :4] - g["out"][:, :4]).max() <= 1.0, np.abs(o[:, :4] - g["out"][:, :4]).max()
+    assert np.abs(o[:, 4:] - g["out"][:, 4:]).max() <= 5e-3
     # train mode returns the raw maps (model/head.py:50-51)
     model.train()
     tr = model(x)
@@ -354,15 +356,22 @@ def test_network_scale_s_640_config1(golden):
     out = model(x.cuda())
     o = out.cpu().numpy()
     assert o.shape == (1, 84, 8400)
-    assert np.abs(o[:, :4, ::16] - g["out_sub"][:, :4]).max() <= 1.5
-    assert np.abs(o[:, 4:, ::16] - g["out_sub"][:, 4:]).max() <= 8e-3
+    print(f"config 1: box err {np.abs(o[:, :4, ::16] - g['out_sub'][:, :4]).max():.4f} px, "
+          f"score err {np.abs(o[:, 4:, ::16] - g['out_sub'][:, 4:]).max():.2e}")
+    assert np.abs(o[:, :4, ::16] - g["out_sub"][:, :4]).max() <= 1.0
+    assert np.abs(o[:, 4:, ::16] - g["out_sub"][:, 4:]).max() <= 5e-3
     db = DecodeBox(80, (640, 640))
     dec = db.decode_box(out)
     dec_np = dec.cpu().numpy()
     want = O.non_max_suppression(dec_np.copy(), 80, (640, 640), (480, 640), True, 0.05, 0.5)
     got = db.non_max_suppression(dec, 80, (640, 640), np.array((480, 640)), True, conf_thres=0.05, nms_thres=0.5)
     assert_dets_equal(got, want)
-    assert got[0] is not None and abs(got[0].shape[0] - int(g["nms_cb_counts"][0])) <= 0.15 * int(g["nms_cb_counts"][0]) + 5
+    # against the reference's own rows for this image (fixture): every reference row has a same-class row of ours that it
+    # overlaps (a bf16 score flip swaps two overlapping survivors); the strict IoU >= 0.9 agreement is printed
+    ref_rows = g["nms_cb_rows"][:int(g["nms_cb_counts"][0])]
+    strict, loose = _match_rate(got[0], ref_rows, 0.9), _match_rate(got[0], ref_rows, 0.5)
+    print(f"config 1 rows: ours {got[0].shape[0]}, reference {len(ref_rows)}, matched at IoU >= 0.9: {strict:.3f}, at IoU >= 0.5: {loose:.3f}")
+    assert got[0] is not None and loose >= 0.95 and strict >= 0.75 and abs(got[0].shape[0] - len(ref_rows)) <= 0.1 * len(ref_rows) + 5
 
 
 def test_detector_graph_matches_eager_and_oracle_nms():
@@ -463,8 +472,8 @@ def test_detector_uint8_pipeline_matches_float_path_and_is_order_safe():
     eng.run_network(xf); eng.run_decode(True, False, False)
     torch.cuda.synchronize()
     o_f = eng.head_out
-    assert float((o_u8[:, :4] - o_f[:, :4]).abs().max()) <= 1.5
-    assert float((o_u8[:, 4:] - o_f[:, 4:]).abs().max()) <= 8e-3
+    assert float((o_u8[:, :4] - o_f[:, :4]).abs().max()) <= 1.0
+    assert float((o_u8[:, 4:] - o_f[:, 4:]).abs().max()) <= 5e-3
 
 
 # ------------------------------------------------------------------------------------------------ f3: device correct_boxes
@@ -545,7 +554,7 @@ def test_sharded_image_ranges_equal_the_single_batch_result():
 
 def test_network_1280_config4_against_live_oracle():
     """BASELINE config 4 geometry (1280x1280: A = 33600, SPPF planes 40x40) at scale n, one image, against the CPU
-    oracle evaluated in the test: boxes <= 1.5 px, scores <= 8e-3; NMS on OUR decoded tensor bit-exact with the oracle's."""
+    oracle evaluated in the test: boxes <= 1 px, scores <= 5e-3; NMS on OUR decoded tensor bit-exact with the oracle's."""
     from oracle import detector_oracle as O, synth
     from transparent_object_detection_b200 import BaseModel, DecodeBox
     C_, d, m = synth.SCALES["n"]
@@ -558,8 +567,8 @@ def test_network_1280_config4_against_live_oracle():
         want = O.forward(sd, x, 80, d)
     o = out.cpu()
     assert tuple(o.shape) == (1, 84, 33600)
-    assert float((o[:, :4] - want[:, :4]).abs().max()) <= 1.5
-    assert float((o[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+    assert float((o[:, :4] - want[:, :4]).abs().max()) <= 1.0
+    assert float((o[:, 4:] - want[:, 4:]).abs().max()) <= 5e-3
     db = DecodeBox(80, (1280, 1280))
     dec = db.decode_box(out)
     want_rows = O.non_max_suppression(dec.cpu().numpy().copy(), 80, (1280, 1280), (720, 1280), True, 0.01, 0.5)
@@ -571,7 +580,7 @@ def test_network_1280_config4_against_live_oracle():
 def test_every_scale_against_live_oracle(scale):
     """All five scales of config.yaml (n (16,1,1.0) ... x (96,3,0.5)): depth 1-3, widths that are not powers
     of two (48, 96, 576 channels), against the CPU oracle evaluated here.  n and s meet the stated absolute tolerance
-    (boxes <= 1.5 px, scores <= 8e-3).  The deeper random-init networks amplify any perturbation (activations reach
+    (features <= 2 % of abs-max, boxes <= 1 px, scores <= 5e-3).  The deeper random-init networks amplify any perturbation (activations reach
     |x| ~ 100 at scale l), so that bf16 STORAGE alone -- the fp32 oracle re-evaluated with the build's rounding points,
     oracle.bf16_emulation -- already deviates from fp32 by up to 15 px / 0.11 in score there; for those the kernel must
     stay within 2.5x that inherent deviation on the raw head maps, and within 4 % of abs-max on every stage feature."""
@@ -594,14 +603,15 @@ def test_every_scale_against_live_oracle(scale):
     assert tuple(out.shape) == tuple(want.shape)
     for name, ref in zip(("p3", "p4", "p5", "h2", "h4", "h6"), list(feats) + list(necks)):
         err = (eng.feature_nchw(name).cpu() - ref).abs()
-        assert float(err.max()) <= 0.04 * float(ref.abs().max()), (name, float(err.max()), float(ref.abs().max()))
+        lim = 0.02 if scale in ("n", "s") else 0.04
+        assert float(err.max()) <= lim * float(ref.abs().max()), (name, float(err.max()), float(ref.abs().max()))
     for i, r in enumerate(eng.raw_maps_nchw()):
         ours = float((r.float().cpu() - raw[i]).abs().max())
         inherent = float((raw_emu[i] - raw[i]).abs().max())
         assert ours <= 2.5 * inherent + 0.02, (i, ours, inherent)
     if scale in ("n", "s"):
-        assert float((out[:, :4] - want[:, :4]).abs().max()) <= 1.5
-        assert float((out[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+        assert float((out[:, :4] - want[:, :4]).abs().max()) <= 1.0
+        assert float((out[:, 4:] - want[:, 4:]).abs().max()) <= 5e-3
 
 
 @pytest.mark.parametrize("nc", [1, 3, 20])
@@ -620,8 +630,8 @@ def test_network_with_few_classes_against_live_oracle(nc):
         want = O.forward(sd, x, nc, d)
     o = out.cpu()
     assert tuple(o.shape) == (2, 4 + nc, 12 * 16 + 6 * 8 + 3 * 4)
-    assert float((o[:, :4] - want[:, :4]).abs().max()) <= 1.5
-    assert float((o[:, 4:] - want[:, 4:]).abs().max()) <= 8e-3
+    assert float((o[:, :4] - want[:, :4]).abs().max()) <= 1.0
+    assert float((o[:, 4:] - want[:, 4:]).abs().max()) <= 5e-3
     db = DecodeBox(nc, (96, 128))
     dec = db.decode_box(out)
     conf = float(dec[:, :, 4:].max()) * 0.5                    # a threshold that keeps some anchors whatever the init
