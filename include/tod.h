@@ -379,6 +379,14 @@ int tod_conv2d_nhwc_bf16_simt_check(const tod_conv_desc* desc, void* stream);
  * counters (16 x uint64 per CTA, see conv_halo_tcgen05.cu) into it; NULL switches recording off. */
 int tod_debug_set_conv_profile(void* d_buf);
 
+/* Debug/profiling helper used by tools only (tools/timeline.py): while d_buf is non-NULL every instrumented kernel that is
+ * ENQUEUED (or captured into a graph) appends one record per CTA {launch id | blockIdx << 32, SM id, %globaltimer at CTA
+ * start, at CTA end} to d_buf = u64 cursor, u64 capacity, then 4 x u64 records: which kernels overlap inside the captured
+ * graph, and how busy each SM is.  tod_debug_timeline_name(id) names launch `id`; NULL switches it off and resets the ids. */
+int tod_debug_set_timeline(void* d_buf);
+int tod_debug_timeline_launches(void);
+const char* tod_debug_timeline_name(int id);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,13 @@ VARIANTS = {
     "halo_bk32": dict(variant=2, bk=32),
     "halo_bk32_m1": dict(variant=2, bk=32, m=1),
     "halo_bk16": dict(variant=2, bk=16),
+    "halo_n64_bk32": dict(variant=2, ncap=64, bk=32),
+    "halo_n64_bk32_m1": dict(variant=2, ncap=64, bk=32, m=1),
+    "halo_n128_bk32": dict(variant=2, ncap=128, bk=32),
+    "halo_n128_bk32_m1": dict(variant=2, ncap=128, bk=32, m=1),
+    "halo_n64_m1": dict(variant=2, ncap=64, m=1),
+    "halo_ring_m1": dict(variant=2, no_station=1, m=1),
+    "halo_ring_m2": dict(variant=2, no_station=1, m=2),
     "halo_noact": dict(variant=2, act=0),        # timing experiments only (results differ by construction)
     "halo_nores": dict(variant=2, nores=1),
 }

@@ -19,7 +19,8 @@ SYMBOLS = (
     "tod_resample_coeffs_bicubic", "tod_letterbox_bicubic_u8", "tod_correct_boxes", "tod_conv2d_tail1x1",
     "tod_conv2d_tail1x1_box_decode", "tod_cbam_workspace_floats", "tod_cbam_nhwc_bf16",
     "tod_softmax_rows_f32_bf16", "tod_attention_fused", "tod_transpose_bf16", "tod_decode_box_from_tuple",
-    "tod_pack_workspace_bytes", "tod_pack_detections",
+    "tod_pack_workspace_bytes", "tod_pack_detections", "tod_debug_set_timeline", "tod_debug_timeline_launches",
+    "tod_debug_timeline_name",
 )
 
 
@@ -135,6 +136,9 @@ def lib() -> C.CDLL:
     L.tod_pack_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]
     L.tod_debug_set_conv_profile.argtypes = [C.c_void_p]
+    L.tod_debug_set_timeline.argtypes = [C.c_void_p]
+    L.tod_debug_timeline_name.argtypes = [C.c_int]
+    L.tod_debug_timeline_name.restype = C.c_char_p
     L.tod_resample_coeffs_bicubic.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.tod_letterbox_bicubic_u8.argtypes = [C.POINTER(LetterboxDesc), C.c_void_p]
     L.tod_conv2d_tail1x1.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvTailDesc), C.c_void_p]

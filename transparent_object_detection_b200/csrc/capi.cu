@@ -21,7 +21,32 @@ int check_cuda(cudaError_t e, const char* what) {
   return TOD_ERR_CUDA;
 }
 
+// ---- timeline (tools only)
+static unsigned long long* g_timeline = nullptr;
+static int g_timeline_seq = 0;
+static char g_timeline_names[4096][48];
+
+TimelineTag timeline_tag(const char* name) {
+  TimelineTag t{g_timeline, 0};
+  if (g_timeline != nullptr) {
+    t.id = g_timeline_seq < 4096 ? g_timeline_seq : 4095;
+    snprintf(g_timeline_names[t.id], sizeof(g_timeline_names[0]), "%s", name);
+    ++g_timeline_seq;
+  }
+  return t;
+}
+
 }  // namespace tod
+
+extern "C" int tod_debug_set_timeline(void* d_buf) {
+  tod::g_timeline = reinterpret_cast<unsigned long long*>(d_buf);
+  if (d_buf == nullptr) tod::g_timeline_seq = 0;
+  return TOD_OK;
+}
+extern "C" int tod_debug_timeline_launches(void) { return tod::g_timeline_seq; }
+extern "C" const char* tod_debug_timeline_name(int id) {
+  return (id >= 0 && id < tod::g_timeline_seq && id < 4096) ? tod::g_timeline_names[id] : "";
+}
 
 extern "C" int tod_version(void) { return 100; }
 

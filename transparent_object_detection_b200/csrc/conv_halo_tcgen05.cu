@@ -77,6 +77,7 @@ struct __align__(64) HaloParams {
   long long mtot;            // batch * hout * wout
   int num_subtiles, m, num_super;
   int reverse;               // TOD_CONV_REVERSE: sub-tile s stands for sub-tile num_subtiles - 1 - s (last image first)
+  int nowait;                // experiment: skip the programmatic-launch wait (TOD_PDL_NOWAIT=1; results are wrong)
   int dyn_w;                 // TOD_CONV_DYNAMIC_W: the weights are an earlier kernel's output (no prefetch before pdl_wait)
   int n_tiles, block_n, cout;
   int block_k, ksteps, chunks, num_taps;
@@ -112,6 +113,7 @@ struct __align__(64) HaloParams {
   const float* bias2;
   uint32_t off_w2, idesc2, hi_w2, hi_stage;
   unsigned long long* prof;  // optional per-CTA wait counters (tools/conv_profile.py), null in production
+  TimelineTag tl;            // optional per-CTA start / end records (tools/timeline.py), null in production
 };
 
 // Profiling helper: accumulates the cycles one role's single issuing thread spends inside a wait.
@@ -309,10 +311,13 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   uint64_t* const p_full_bar = &tail_bars[TAIL ? 1 : 0];
   uint64_t* const d2_full_bar = &tail_bars[TAIL ? 3 : 0];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ unsigned long long tl_marks[2];   // timeline: programmatic wait returned / first accumulator complete
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const unsigned long long tl_t0 = (p.tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
+  if (p.tl.buf != nullptr && threadIdx.x == 0) tl_marks[0] = tl_marks[1] = 0;
 
   // persistent schedule: this CTA owns N tile `nt`.  Full rounds are interleaved (CTA g takes super-tile r * G + g, so
   // the grid streams through adjacent memory together); what is left after the last full round is split evenly at
@@ -390,7 +395,8 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       // Everything above (and the weights just requested) is independent of earlier kernels.  Activations, residual
       // and upsample-add operands and the output buffer are not: every access to them in this grid is ordered after
       // this wait through the mbarrier chain that starts at the first A load below.
-      pdl_wait();
+      if (!p.nowait) pdl_wait();
+      if (p.tl.buf != nullptr) tl_marks[0] = global_timer_ns();
       if (p.stationary && p.dyn_w) load_resident_weights();   // "weights" produced by the previous kernel (q . k^T)
       int ai = 0, bi = 0;
       uint32_t pha = 0, phb = 0;   // ring phase bits
@@ -794,7 +800,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     };
     // The extra operand was written by an earlier kernel and its first chunk is requested BEFORE the accumulator wait
     // (the loads do not depend on this grid's MMAs), so these threads order themselves after the earlier grids directly.
-    if (EXTRA != 0 && EXTRA != 7 && EXTRA != 8) pdl_wait();
+    if (EXTRA != 0 && EXTRA != 7 && EXTRA != 8 && !p.nowait) pdl_wait();
     const int first_cols = min(32, p.block_n);
     int tj = 0;   // EXTRA 7: sub-tiles this group has sent through the tail
     uint32_t lt = 0;
@@ -846,6 +852,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
       wc.end(1, tw);
+      if (p.tl.buf != nullptr && it == 0 && leader) tl_marks[1] = global_timer_ns();
       tcgen05_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < m_cur; ++mt) {
@@ -1022,6 +1029,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1]);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -1333,7 +1341,13 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.act = d->act;
   p.reverse = (d->flags & TOD_CONV_REVERSE) ? 1 : 0;
   p.dyn_w = (d->flags & TOD_CONV_DYNAMIC_W) ? 1 : 0;
+  p.nowait = pdl_nowait();
   p.prof = g_prof;
+  {
+    char nm[48];
+    snprintf(nm, sizeof(nm), "conv %d>%d k%d s%d @%dx%d%s", d->cin, d->cout, d->ksize, d->stride, hout, wout, tail ? " +tail" : "");
+    p.tl = timeline_tag(nm);
+  }
   *smem_bytes = smem;
   return TOD_OK;
 }

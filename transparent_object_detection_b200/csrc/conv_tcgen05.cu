@@ -49,6 +49,8 @@ struct __align__(64) ConvKernelParams {
   int up_h, up_w;          // real output dims for the upsample-add (flat mode needs them)
   int act, out_f32;
   int reverse;             // TOD_CONV_REVERSE: walk the tiles from the last to the first
+  int nowait;              // experiment: skip the programmatic-launch wait (TOD_PDL_NOWAIT=1; results are wrong)
+  TimelineTag tl;          // optional per-CTA start / end records (tools/timeline.py)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t desc_hi) {
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ unsigned long long tl_marks[2];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const unsigned long long tl_t0 = (p.tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
+  if (p.tl.buf != nullptr && threadIdx.x == 0) tl_marks[0] = tl_marks[1] = 0;
   const int num_chunks = p.num_taps * p.chunks_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -158,7 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
     if (elect_one()) {
       // every access of this grid to data of earlier kernels (activations, residual / upsample-add, the output buffer)
       // is ordered after this wait through the mbarrier chain that starts at the first load below
-      pdl_wait();
+      if (!p.nowait) pdl_wait();
+      if (p.tl.buf != nullptr) tl_marks[0] = global_timer_ns();
       int s = 0;         // ring slot and phase, continue across tiles
       uint32_t ph = 0;
       for (int tile_i = blockIdx.x; tile_i < p.total_tiles; tile_i += gridDim.x) {
@@ -256,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
       const __nv_bfloat16* res_ptr = p.residual ? p.residual + pix * p.res_pitch : nullptr;
 
       mbar_wait(&tmem_full_bar[group], (lt >> 1) & 1);
+      if (p.tl.buf != nullptr && lt == 0 && r == 0) tl_marks[1] = global_timer_ns();
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * p.block_n;
       int c = 0;
@@ -288,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_tcgen05(const __grid_c
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -572,6 +580,12 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
   p.act = d->act;
   p.out_f32 = d->out_dtype == TOD_OUT_F32;
   p.reverse = (d->flags & TOD_CONV_REVERSE) ? 1 : 0;
+  p.nowait = pdl_nowait();
+  {
+    char nm[48];
+    snprintf(nm, sizeof(nm), "tapconv %d>%d k%d s%d @%dx%d", d->cin, d->cout, d->ksize, d->stride, hout, wout);
+    p.tl = timeline_tag(nm);
+  }
 
   const long long m_tiles = static_cast<long long>(d->ksize == 1 ? 1 : d->batch) * p.tiles_h * p.tiles_w;
   p.n_tiles = ceil_div(d->cout, block_n);

@@ -110,7 +110,8 @@ __device__ __forceinline__ unsigned int score_desc_bits(float s) {
 
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __restrict__ cand_conf,
                                                                 const int* __restrict__ cand_cls, int anchors,
-                                                                float conf_thres, NmsWork wk, int a_pow2) {
+                                                                float conf_thres, NmsWork wk, int a_pow2, const TimelineTag tl) {
+  const unsigned long long tl_t0 = (tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
   extern __shared__ unsigned long long sort_smem[];
   __shared__ int s_count;
   const int b = blockIdx.x;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
   }
   __syncthreads();
   if (threadIdx.x == 0) wk.n_seg[b] = s_count;
+  if (threadIdx.x == 0) timeline_write(tl, tl_t0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,7 +336,8 @@ __device__ __forceinline__ void nms_cta_segment(const float4* boxes, const int* 
 }
 
 __global__ void __launch_bounds__(kSegWarps * 32) nms_segment_kernel(const float4* __restrict__ cand_box, int anchors,
-                                                                     float iou_thr, NmsWork wk) {
+                                                                     float iou_thr, NmsWork wk, const TimelineTag tl) {
+  const unsigned long long tl_t0 = (tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
   // pass 1 uses the union as per-warp kept lists [kSegWarps][kWarpSegMax], pass 2 as staged boxes + flags of one segment
   __shared__ __align__(16) unsigned char s_union[kCtaSegSmem * (sizeof(float4) + 1)];
   __shared__ float4 s_kept[32];
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__(kSegWarps * 32) nms_segment_kernel(const float
       nms_cta_segment<false>(boxes, order + s0, flags_img + s0, len, iou_thr, s_kept, s_tilepos, s_ctl);
     }
   }
+  if (threadIdx.x == 0) timeline_write(tl, tl_t0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -580,10 +584,10 @@ extern "C" int tod_nms(const float* d_cand_box, const float* d_cand_conf, const 
     if (rc != TOD_OK) return rc;
     attr_once.done();
   }
-  nms_sort_kernel<<<batch, kSortThreads, sort_smem, st>>>(d_cand_conf, d_cand_cls, anchors, conf_thres, wk, ap2);
+  nms_sort_kernel<<<batch, kSortThreads, sort_smem, st>>>(d_cand_conf, d_cand_cls, anchors, conf_thres, wk, ap2, timeline_tag("nms sort"));
   TOD_CHECK_LAUNCH("nms_sort_kernel launch");
   nms_segment_kernel<<<dim3(kSegCtasPerImage, batch), kSegWarps * 32, 0, st>>>(
-      reinterpret_cast<const float4*>(d_cand_box), anchors, thr_f, wk);
+      reinterpret_cast<const float4*>(d_cand_box), anchors, thr_f, wk, timeline_tag("nms segments"));
   TOD_CHECK_LAUNCH("nms_segment_kernel launch");
   nms_compact_kernel<<<batch, 256, 0, st>>>(reinterpret_cast<const float4*>(d_cand_box), d_cand_conf, d_cand_cls, anchors,
                                             wk, d_keep_idx, d_keep_count, d_dets);

@@ -72,7 +72,8 @@ constexpr int kFastElems = 4;
 
 template <int VEC>
 __global__ void __launch_bounds__(kPoolThreads) sppf_pool_fast_kernel(__nv_bfloat16* __restrict__ buf, int h, int w, int c,
-                                                                      int pitch) {
+                                                                      int pitch, const TimelineTag tl) {
+  const unsigned long long tl_t0 = (tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
   extern __shared__ uint4 pool_smem[];
   const int total = h * w * VEC;            // <= kFastElems * kPoolThreads (host)
   uint4* b0 = pool_smem;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_fast_kernel(__nv_bfloa
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) timeline_write(tl, tl_t0);
 }
 
 }  // namespace tod
@@ -153,13 +155,13 @@ extern "C" int tod_sppf_pool_nhwc_bf16(void* d_buf, int32_t batch, int32_t h, in
   auto st = static_cast<cudaStream_t>(stream);
   if (c % 16 == 0 && h * w * 2 <= kFastElems * kPoolThreads) {
     sppf_pool_fast_kernel<2><<<batch * (c / 16), kPoolThreads, 2 * 2 * plane16, st>>>(
-        reinterpret_cast<__nv_bfloat16*>(d_buf), h, w, c, pitch);
+        reinterpret_cast<__nv_bfloat16*>(d_buf), h, w, c, pitch, timeline_tag("sppf pool"));
     TOD_CHECK_LAUNCH("sppf_pool_fast_kernel launch");
     return TOD_OK;
   }
   if (h * w <= kFastElems * kPoolThreads) {
     sppf_pool_fast_kernel<1><<<batch * (c / 8), kPoolThreads, 2 * plane16, st>>>(reinterpret_cast<__nv_bfloat16*>(d_buf), h, w,
-                                                                                c, pitch);
+                                                                                c, pitch, timeline_tag("sppf pool"));
     TOD_CHECK_LAUNCH("sppf_pool_fast_kernel launch");
     return TOD_OK;
   }

@@ -185,7 +185,8 @@ __device__ __forceinline__ float byte_to_float(uint32_t word) {
 template <int COUT>
 __global__ void __launch_bounds__(kStemU8Threads) stem_u8_tma_kernel(const __grid_constant__ StemTma tm, int tiles_w, int tiles_h,
                                                                     int num_tiles,
-                                                                    const __grid_constant__ StemU8Weights<COUT> wt) {
+                                                                    const __grid_constant__ StemU8Weights<COUT> wt, const TimelineTag tl) {
+  const unsigned long long tl_t0 = (tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
   constexpr uint32_t kCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : 128);
   constexpr int kStageC = COUT <= 64 ? COUT : (COUT % 64 == 0 ? 64 : 48);   // channels staged per epilogue pass
   constexpr int kRowBytes = kStageC * 2;                    // one staged output pixel
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(kStemU8Threads) stem_u8_tma_kernel(const __gri
     tcgen05_fence_after();
     tmem_dealloc(tmem, kCols);
   }
+  if (t == 0) timeline_write(tl, tl_t0);
 }
 
 template <int COUT>
@@ -428,7 +430,7 @@ static int launch_stem_u8(const uint8_t* d_x, const float* h_w, const float* h_b
     long long blocks = static_cast<long long>(sms) * per_sm;
     if (blocks > ntiles) blocks = ntiles;
     stem_u8_tma_kernel<COUT><<<static_cast<unsigned>(blocks), kStemU8Threads, 0, st>>>(tm, tiles_w, tiles_h,
-                                                                                        static_cast<int>(ntiles), wt);
+                                                                                        static_cast<int>(ntiles), wt, timeline_tag("stem u8"));
     TOD_CHECK_LAUNCH("stem_u8_tma_kernel launch");
     return TOD_OK;
   }

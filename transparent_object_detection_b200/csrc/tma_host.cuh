@@ -69,6 +69,17 @@ inline bool pdl_enabled() {
   return on == 1;
 }
 
+// EXPERIMENT ONLY (results are wrong: races): TOD_PDL_NOWAIT=1 makes the conv kernels skip griddepcontrol.wait, which bounds
+// from above what tile-granular inter-layer dependencies could gain over the grid-wide wait.
+inline int pdl_nowait() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TOD_PDL_NOWAIT");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return on;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

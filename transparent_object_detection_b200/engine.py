@@ -318,7 +318,7 @@ class DetectorEngine:
         ncp = (nc + 15) // 16 * 16           # class conv output padded to the MMA N granularity
         self.raw_pitch = 64 + ncp
         self.raw: List[torch.Tensor] = []
-        fuse_head0 = os.environ.get("TOD_FUSE_HEAD0", "0") == "1" and not self.attention   # (a CBAM follows each .0 otherwise)
+        fuse_head0 = os.environ.get("TOD_FUSE_HEAD0", "1") != "0" and not self.attention   # (a CBAM follows each .0 otherwise)
         for i, f in enumerate(feats):
             raw = torch.zeros((B, f.h, f.w, self.raw_pitch), dtype=torch.float32, device=dev)
             self.raw.append(raw)
