@@ -244,7 +244,7 @@ def run_config3(args, rank, local_rank, world):
     det = Detector(model, (args.size, args.size), confidence=CONF, nms_iou=IOU, letterbox_image=True, pipeline_depth=args.depth)
     B, total = args.batch, args.images
     assert total % B == 0
-    lo, hi = shard_range(total, world, rank)
+    lo, hi = shard_range(total, rank, world)
     assert lo % B == 0 and hi % B == 0, "image ranges must be whole batches"
 
     def host_batch(j):
@@ -278,12 +278,7 @@ def run_config3(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall, t_rank_max = float(t[0]), float(t[1])
     tg = time.perf_counter()
-    if world > 1:
-        parts = [None] * world if rank == 0 else None
-        dist.gather_object(rows, parts, dst=0)
-        gathered = gather_detections(parts) if rank == 0 else None
-    else:
-        gathered = gather_detections([rows])
+    gathered = gather_detections(rows)          # host-side object gather to rank 0, rank order (sharding.py)
     gather_s = time.perf_counter() - tg
     if rank == 0:
         assert len(gathered) == total

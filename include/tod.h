@@ -82,6 +82,8 @@ typedef struct tod_conv_desc {
 /* Walk the output tiles from the last image to the first.  Consecutive layers of the plan alternate direction so that a
  * layer starts on the activations its producer wrote last, which are the ones still resident in the 126 MB L2. */
 #define TOD_CONV_REVERSE 2
+/* Tests / tools: keep the 16x8 pixel patches where the plan would pick row-flat tiles (both give bit-identical outputs). */
+#define TOD_CONV_PATCH_TILES 4
 
 int tod_conv2d_nhwc_bf16(const tod_conv_desc* desc, void* stream);
 

@@ -21,7 +21,7 @@ def run_conv(x_buf: torch.Tensor, x_off: int, cin: int, w: torch.Tensor, bias: O
              out_buf: torch.Tensor, out_off: int, stride: int = 1, act: int = 1,
              residual: Optional[torch.Tensor] = None, res_off: int = 0, upadd: Optional[torch.Tensor] = None,
              block_k: int = 0, num_stages: int = 0, simt: bool = False, variant: int = 0, m: int = 0,
-             no_station: int = 0):
+             no_station: int = 0, flags: int = 0):
     """x_buf bf16 (B, H, W, pitch) cuda; w f32 (cout, cin, k, k); out_buf bf16|f32 (B, Ho, Wo, pitch)."""
     L = _lib.lib()
     cout, _, k, _ = w.shape
@@ -42,6 +42,7 @@ def run_conv(x_buf: torch.Tensor, x_off: int, cin: int, w: torch.Tensor, bias: O
     d.out_dtype = 1 if out_buf.dtype == torch.float32 else 0
     d.block_k, d.num_stages = block_k, num_stages
     d.reserved[0], d.reserved[1], d.reserved[2] = variant, m, no_station   # kernel variant knobs (conv_tcgen05.cu)
+    d.flags = flags
     fn = L.tod_conv2d_nhwc_bf16_simt_check if simt else L.tod_conv2d_nhwc_bf16
     check(fn(C.byref(d), stream()), "conv")
     torch.cuda.synchronize()

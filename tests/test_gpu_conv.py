@@ -53,6 +53,16 @@ CASES = [
     ("1x1_upadd_n512_two_ntiles", 1, 20, 12, 64, 512, 1, 1, {"upadd": True}),
     ("1x1_upadd_n32_register_path", 1, 12, 12, 64, 32, 1, 1, {"upadd": True}),
     ("1x1_upadd_noact_register_path", 1, 16, 16, 64, 64, 1, 1, {"upadd": True, "act": 0}),
+    # row-flat tiles (3x3 stride 1 on maps that 16x8 patches tile badly): one tile per image, ragged last tile, residual
+    # through the ring and through registers, channel windows, N tiles of 128 chosen by the plan, narrow K chunks
+    ("3x3_flat_10x10_n96", 3, 10, 10, 64, 96, 3, 1, {}),
+    ("3x3_flat_18x20_res_views", 2, 18, 20, 64, 64, 3, 1, {"x_pitch": 192, "x_off": 64, "out_pitch": 160, "out_off": 32,
+                                                           "residual": True}),
+    ("3x3_flat_20x20_n512", 1, 20, 20, 128, 512, 3, 1, {}),
+    ("3x3_40x40_c256_res", 1, 40, 40, 256, 256, 3, 1, {"residual": True}),
+    ("3x3_flat_20x12_rect_c32", 2, 20, 12, 32, 32, 3, 1, {"residual": True}),
+    ("3x3_flat_17x9_c16_f32", 1, 17, 9, 16, 48, 3, 1, {"f32": True, "act": 0}),
+    ("3x3_flat_126wide", 1, 4, 126, 32, 64, 3, 1, {}),
 ]
 VARIANTS = {"pertap": 1, "halo": 2}
 
@@ -115,6 +125,26 @@ def test_simt_check_kernel_matches_reference(case_def):
     assert rep["bad_frac"] == 0 and rep["nan"] == 0, rep
 
 
+@pytest.mark.parametrize("case_def", [c for c in CASES if c[6] == 3 and c[7] == 1], ids=lambda c: c[0])
+def test_flat_tiles_reverse_order_and_patch_tiles_are_bit_identical(case_def):
+    """The tile geometry (row-flat tiles vs 16x8 patches, TOD_CONV_PATCH_TILES) and the tile order (TOD_CONV_REVERSE) only
+    change WHICH CTA computes a pixel and when: the MMA sequence per output element is the same, so the outputs of the halo
+    kernel must be bit-identical in all four combinations."""
+    from tests import gpu_util as U
+    from transparent_object_detection_b200._lib import TOD_CONV_PATCH_TILES, TOD_CONV_REVERSE
+    name, B, H, W, cin, cout, k, s, opts = case_def
+    case = make_case(B, H, W, cin, cout, k, s, opts)
+    outs = []
+    for flags in (0, TOD_CONV_PATCH_TILES, TOD_CONV_REVERSE, TOD_CONV_PATCH_TILES | TOD_CONV_REVERSE):
+        out = torch.full_like(case["out"], 7.0)
+        U.run_conv(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], out, case["out_off"], case["stride"],
+                   case["act"], case["res"], case["res_off"], case["up"], 0, case["stages"], variant=2, m=case["m"],
+                   no_station=case["no_station"], flags=flags)
+        outs.append(out)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 def test_conv_rejects_bad_arguments():
     import ctypes as C
     from transparent_object_detection_b200 import _lib
@@ -134,6 +164,8 @@ def test_conv_rejects_bad_arguments():
 
 # ------------------------------------------------------------------------------------------ fused 1x1 tail (back-to-back GEMM)
 TAIL_CASES = [
+    ("3x3_flat_20x20_c64", 2, 20, 20, 64, 3, 1),    # row-flat tiles under the fused tail (head.box.2.2 geometry)
+    ("3x3_flat_10x10_c128", 3, 10, 10, 128, 3, 1),
     ("3x3s2_c32_160", 2, 160, 160, 32, 3, 2),      # backbone.dark2.0 -> dark2.1.cv1 geometry (scale s)
     ("3x3s2_c32_ragged", 1, 40, 56, 32, 3, 2),
     ("3x3_c64", 2, 24, 40, 64, 3, 1),

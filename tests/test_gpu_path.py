@@ -583,7 +583,7 @@ def test_every_scale_against_live_oracle(scale):
     (features <= 2 % of abs-max, boxes <= 1 px, scores <= 5e-3).  The deeper random-init networks amplify any perturbation (activations reach
     |x| ~ 100 at scale l), so that bf16 STORAGE alone -- the fp32 oracle re-evaluated with the build's rounding points,
     oracle.bf16_emulation -- already deviates from fp32 by up to 15 px / 0.11 in score there; for those the kernel must
-    stay within 2.5x that inherent deviation on the raw head maps, and within 4 % of abs-max on every stage feature."""
+    stay within 2.5x that inherent deviation on the raw head maps and on every stage feature (or 4 % of abs-max)."""
     from oracle import detector_oracle as O, synth
     from transparent_object_detection_b200 import BaseModel
     C_, d, m = synth.SCALES[scale]
@@ -599,12 +599,15 @@ def test_every_scale_against_live_oracle(scale):
         raw = O.head_raw(sd, necks)
         want = O.head_decode(raw, 80)
         with O.bf16_emulation():
-            raw_emu = O.head_raw(sd, O.neck(sd, O.backbone(sd, x, d), d))
+            feats_emu = O.backbone(sd, x, d)
+            necks_emu = O.neck(sd, feats_emu, d)
+            raw_emu = O.head_raw(sd, necks_emu)
     assert tuple(out.shape) == tuple(want.shape)
-    for name, ref in zip(("p3", "p4", "p5", "h2", "h4", "h6"), list(feats) + list(necks)):
-        err = (eng.feature_nchw(name).cpu() - ref).abs()
-        lim = 0.02 if scale in ("n", "s") else 0.04
-        assert float(err.max()) <= lim * float(ref.abs().max()), (name, float(err.max()), float(ref.abs().max()))
+    for name, ref, emu in zip(("p3", "p4", "p5", "h2", "h4", "h6"), list(feats) + list(necks), list(feats_emu) + list(necks_emu)):
+        err = float((eng.feature_nchw(name).cpu() - ref).abs().max())
+        inherent = float((emu - ref).abs().max())                  # what bf16 storage alone costs at this stage
+        lim = 0.02 * float(ref.abs().max()) if scale in ("n", "s") else max(0.04 * float(ref.abs().max()), 2.5 * inherent)
+        assert err <= lim, (name, err, inherent, float(ref.abs().max()))
     for i, r in enumerate(eng.raw_maps_nchw()):
         ours = float((r.float().cpu() - raw[i]).abs().max())
         inherent = float((raw_emu[i] - raw[i]).abs().max())

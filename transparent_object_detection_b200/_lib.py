@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
     ]
 
 
-TOD_CONV_DYNAMIC_W, TOD_CONV_REVERSE = 1, 2
+TOD_CONV_DYNAMIC_W, TOD_CONV_REVERSE, TOD_CONV_PATCH_TILES = 1, 2, 4
 
 
 class DecodeDesc(C.Structure):

@@ -70,9 +70,12 @@ struct __align__(64) HaloParams {
   CUtensorMap tm_out;
   CUtensorMap tm_res;        // residual panels (EXTRA 5: TMA ring in shared memory), same boxes / swizzle as tm_out
   // geometry
-  int patch_mode;            // 1: 16x8 pixel patches (3x3), 0: 128 consecutive pixels (1x1)
+  int patch_mode;            // 1: 16x8 pixel patches (3x3), 0: 128 consecutive pixels (1x1), 2: row-flat tiles (3x3 s1 on small maps)
   int hout, wout;
   int tiles_w, tiles_per_img;
+  int tile_w_step, tile_h_step;   // first output column / row of tile (tx, ty) = tx * tile_w_step, ty * tile_h_step
+  int patch_cols, rows_valid;     // accumulator row r <-> pixel (r / patch_cols, r % patch_cols) of the tile, r < rows_valid
+  FastDiv fd_patch_cols;
   FastDiv fd_tiles_per_img, fd_tiles_w, fd_wout, fd_hw;
   long long mtot;            // batch * hout * wout
   int num_subtiles, m, num_super;
@@ -420,8 +423,8 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
               const int img = p.fd_tiles_per_img.div(s);
               const int rem = s - img * p.tiles_per_img;
               const int ti = p.fd_tiles_w.div(rem);
-              c1 = (rem - ti * p.tiles_w) * kPatchW;
-              c2 = ti * kPatchH;
+              c1 = (rem - ti * p.tiles_w) * p.tile_w_step;
+              c2 = ti * p.tile_h_step;
               c3 = img;
             } else {
               c1 = s * 128;
@@ -641,6 +644,10 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     const int group = (warp - 2) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // accumulator row = pixel within the sub-tile
+    // pixel of row r inside a tile: (r / 8, r % 8) in a 16 x 8 patch, (r / patch_cols, r % patch_cols) in a row-flat tile
+    const int rh = p.patch_mode == 2 ? p.fd_patch_cols.div(r) : (r >> 3);
+    const int rw = p.patch_mode == 2 ? r - rh * p.patch_cols : (r & 7);
+    const bool r_valid = r < p.rows_valid;
     const bool leader = q == 0 && lane == 0;   // one thread per group issues the TMA stores
     const uint32_t stage = smem_base + p.off_stage + group * kStageBytes;
     const uint32_t bar_id = 1 + group;
@@ -765,12 +772,12 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         const int img = p.fd_tiles_per_img.div(s);
         const int rem = s - img * p.tiles_per_img;
         const int ti = p.fd_tiles_w.div(rem);
-        c1 = (rem - ti * p.tiles_w) * kPatchW;
-        c2 = ti * kPatchH;
+        c1 = (rem - ti * p.tiles_w) * p.tile_w_step;
+        c2 = ti * p.tile_h_step;
         c3 = img;
         if (EXTRA == 1 || EXTRA == 2) {
-          const int h = c2 + (r >> 3), w = c1 + (r & 7);
-          if (h < p.hout && w < p.wout) {
+          const int h = c2 + rh, w = c1 + rw;
+          if (r_valid && h < p.hout && w < p.wout) {
             if (EXTRA == 1)
               ex_row = p.residual + ((static_cast<long long>(img) * p.hout + h) * p.wout + w) * p.res_pitch + n0;
             else
@@ -975,8 +982,8 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
               }
             }
             tcgen05_fence_before();
-            const int ah = c2 + (r >> 3), aw = c1 + (r & 7);
-            if (ah < p.hout && aw < p.wout) {
+            const int ah = c2 + rh, aw = c1 + rw;
+            if (r_valid && ah < p.hout && aw < p.wout) {
               const size_t g = static_cast<size_t>(c3) * p.dec_anchors + p.dec_level_off + ah * p.wout + aw;
               const float4 bpx = box_xywh_px(dist[0], dist[1], dist[2], dist[3], aw, ah, p.dec_stride);
               reinterpret_cast<float4*>(p.cand_box)[g] = box_corners_norm(bpx, p.dec_in_w, p.dec_in_h);
@@ -1045,7 +1052,7 @@ static uint32_t desc_hi(uint32_t sbo_bytes, int bk) {
 // res_ring: 0 none, 1 bf16 residual panels, 2 f32 upsample-add panels (1x1 conv on 16x8 pixel tiles) through the
 // shared-memory TMA ring of the epilogue groups.
 static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits,
-                        int res_ring = 0, bool tail = false) {
+                        int res_ring = 0, bool tail = false, double* cost_out = nullptr) {
   int rc;
   *fits = true;
   memset(&p, 0, sizeof(p));
@@ -1094,10 +1101,30 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     p.num_subtiles = static_cast<int>((mtot + 127) / 128);
     p.tiles_w = 1;
     p.tiles_per_img = 1;
+    p.patch_cols = kPatchW;
+    p.rows_valid = 128;
   } else {
-    p.patch_mode = 1;
-    p.tiles_w = ceil_div(wout, kPatchW);
-    p.tiles_per_img = p.tiles_w * ceil_div(hout, kPatchH);
+    // Row-flat tiles (3x3 stride 1 on small maps): a tile is `rt` whole output rows of (wout + 2) positions -- the two extra
+    // positions per row are the halo columns, computed and never stored -- so that accumulator row r is simply the r-th
+    // position in row-major order and a tap (kh, kw) is the SAME flat run of shared-memory rows shifted by kh * (wout + 2)
+    // + kw: any map whose width is not a multiple of 8 / height not a multiple of 16 tiles far better this way
+    // (20x20: 4 tiles of 5 rows per image instead of 6 patches of 16x8, i.e. 78 % instead of 52 % useful MMA rows;
+    // 40x40: 14 tiles of 3 rows, 89 % instead of 83 %).
+    const int flat_cols = wout + 2, flat_rt = flat_cols <= 128 ? 128 / flat_cols : 0;
+    bool flat = false;
+    if (d->ksize == 3 && d->stride == 1 && res_ring != 2 && flat_rt >= 1 && flat_tiles_enabled() && !(d->flags & TOD_CONV_PATCH_TILES)) {
+      // taken when it saves at least a fifth of the tiles: a flat tile's patch is ~17 % larger than a 16x8 one, and at
+      // 40x40 (14 tiles instead of 15) the shared memory that costs the weight ring made the layer slower (49 vs 37 us)
+      const long long patch_tiles = static_cast<long long>(ceil_div(wout, kPatchW)) * ceil_div(hout, kPatchH);
+      flat = ceil_div(hout, flat_rt) * 100ll <= patch_tiles * 80ll;
+    }
+    p.patch_mode = flat ? 2 : 1;
+    p.tiles_w = flat ? 1 : ceil_div(wout, kPatchW);
+    p.tiles_per_img = flat ? ceil_div(hout, flat_rt) : p.tiles_w * ceil_div(hout, kPatchH);
+    p.tile_w_step = flat ? 0 : kPatchW;
+    p.tile_h_step = flat ? flat_rt : kPatchH;
+    p.patch_cols = flat ? flat_cols : kPatchW;
+    p.rows_valid = flat ? flat_rt * flat_cols : 128;
     const long long nsub = static_cast<long long>(d->batch) * p.tiles_per_img;
     TOD_CHECK_ARG(nsub < (1ll << 30), "conv: too many tiles");
     p.num_subtiles = static_cast<int>(nsub);
@@ -1113,6 +1140,28 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
       p.tap_a_off[0] = 0;
       p.tap_hi_a[0] = desc_hi(8 * rb, bk);
       sub_bytes = 128 * rb;
+    } else if (flat) {
+      const int ph = flat_rt + 2;                      // rows of the loaded box: the tile's rows plus one halo row each side
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
+                                static_cast<uint64_t>(d->hin), static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {px, px * d->win, px * d->win * d->hin};
+      const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(flat_cols), static_cast<uint32_t>(ph), 1};
+      if ((rc = encode_map(&p.tm_a[0], d->d_x, 4, dims, str, box, swz_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_in)) != TOD_OK) return rc;
+      p.n_aloads = 1;
+      p.al_map[0] = 0;
+      p.al_dw[0] = -1;
+      p.al_dh[0] = -1;
+      p.al_off[0] = 0;
+      p.a_tx_bytes = flat_cols * ph * rb;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          p.tap_a_off[kh * 3 + kw] = (kh * flat_cols + kw) * rb;
+          p.tap_hi_a[kh * 3 + kw] = desc_hi(8 * rb, bk);     // consecutive rows: the canonical 8-row group stride
+        }
+      // the 128 accumulator rows of the last tap read rows [2 * cols + 2, 2 * cols + 130): past the loaded box for the
+      // unused rows >= rows_valid (stale shared memory, never stored) -- the slot must cover them
+      sub_bytes = (2 * flat_cols + 2 + 128) * rb;
+      if (sub_bytes < p.a_tx_bytes) sub_bytes = p.a_tx_bytes;
     } else if (d->stride == 1) {
       const int pw = kPatchW + 2, ph = kPatchH + 2;
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->win),
@@ -1179,6 +1228,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     };
     const bool ok = make_fd(p.tiles_per_img, p.num_subtiles, &p.fd_tiles_per_img) &&
                     make_fd(p.tiles_w, p.tiles_per_img, &p.fd_tiles_w) &&
+                    make_fd(p.patch_cols > 0 ? p.patch_cols : 1, 128, &p.fd_patch_cols) &&
                     make_fd(wout, static_cast<long long>(hout) * wout, &p.fd_wout) &&
                     make_fd(static_cast<long long>(hout) * wout, mtot, &p.fd_hw);
     TOD_CHECK_ARG(ok, "conv: problem too large for the tile index arithmetic");
@@ -1210,7 +1260,8 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(wout), static_cast<uint64_t>(hout),
                                 static_cast<uint64_t>(d->batch)};
       const uint64_t str[3] = {opx, opx * wout, opx * wout * hout};
-      const uint32_t box[4] = {static_cast<uint32_t>(pc), kPatchW, kPatchH, 1};
+      const uint32_t box[4] = {static_cast<uint32_t>(pc), static_cast<uint32_t>(p.patch_mode == 2 ? p.patch_cols : kPatchW),
+                               static_cast<uint32_t>(p.patch_mode == 2 ? p.tile_h_step : kPatchH), 1};
       if ((rc = encode_map(&p.tm_out, d->d_out, 4, dims, str, box, swz_out, dt)) != TOD_OK) return rc;
     } else {
       const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
@@ -1244,9 +1295,10 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(wout), static_cast<uint64_t>(hout),
                                 static_cast<uint64_t>(d->batch)};
       const uint64_t str[3] = {rpx, rpx * wout, rpx * wout * hout};
-      const uint32_t box[4] = {static_cast<uint32_t>(p.pc), kPatchW, kPatchH, 1};
+      const uint32_t bw = p.patch_mode == 2 ? p.patch_cols : kPatchW, bh = p.patch_mode == 2 ? p.tile_h_step : kPatchH;
+      const uint32_t box[4] = {static_cast<uint32_t>(p.pc), bw, bh, 1};
       if ((rc = encode_map(&p.tm_res, d->d_residual, 4, dims, str, box, swz_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, promo_res)) != TOD_OK) return rc;
-      p.res_tx_bytes = static_cast<uint32_t>(p.pb) * kPatchW * kPatchH;
+      p.res_tx_bytes = static_cast<uint32_t>(p.pb) * bw * bh;
     } else {
       const uint32_t rows = mtot < 128 ? static_cast<uint32_t>(mtot) : 128u;
       const uint64_t dims[4] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(mtot), 1, 1};
@@ -1319,6 +1371,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     *fits = false;
     return TOD_OK;
   }
+  if (cost_out != nullptr) *cost_out = best_cost * p.n_tiles;   // L2 -> SM bytes per output pixel over all N tiles
   if (d->num_stages > 0 && d->num_stages < p.sa) p.sa = d->num_stages;
   p.a_slot_bytes = p.m * p.sub_bytes;
   p.off_b = p.sa * p.a_slot_bytes;
@@ -1421,10 +1474,27 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
     if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 2)) != TOD_OK) return rc;
     if (fits) kvar = 11;
   }
+  double cost = 0.0;
   for (int bk = bk0; bk >= 16 && !fits; bk >>= 1)
-    if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits)) != TOD_OK) return rc;
+    if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits, 0, false, &cost)) != TOD_OK) return rc;
   TOD_CHECK_ARG(fits, "conv: no shared-memory plan fits (cin %d cout %d ksize %d stride %d)", d->cin, d->cout, d->ksize,
                 d->stride);
+  if (kvar != 10 && kvar != 11 && fuse == nullptr && d->ksize == 3 && d->cout > 128 && d->reserved[3] == 0) {
+    // wide 3x3 layers: two N tiles of <= 128 columns let TWO sub-tiles share every streamed weight tile (m = 2 within the
+    // 512 TMEM columns) at the price of reading the activations twice -- taken when the plan's L2 -> SM bytes per output
+    // pixel are lower (256 -> 256 3x3 @20x20: 774 vs 1272 KB per 128 pixels; measured 56 vs 73 us)
+    tod_conv_desc d2 = *d;
+    d2.reserved[3] = 128;
+    HaloParams p2;
+    size_t smem2 = 0;
+    bool fits2 = false;
+    double cost2 = 0.0;
+    if ((rc = build_params(&d2, p.block_k, cin_pad, p2, &smem2, &fits2, 0, false, &cost2)) != TOD_OK) return rc;
+    if (fits2 && cost2 < cost * 0.9) {
+      p = p2;
+      smem = smem2;
+    }
+  }
 
   if (fuse != nullptr) {
     TOD_CHECK_ARG(p.n_tiles == 1 && !p.patch_mode, "fused head decode: unexpected tiling");

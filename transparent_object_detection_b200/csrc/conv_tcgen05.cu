@@ -447,8 +447,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
     const long long mtot = static_cast<long long>(d->batch) * (d->hin / d->stride) * wout;
     bool halo;
     if (d->ksize == 3 && d->stride == 2) halo = d->cin <= 32;
-    else if (d->ksize == 3) halo = wout >= 40;   // (wide-K / narrow-N layers went to the per-tap kernel until the halo
-                                                 // kernel's MMA role was unrolled: 256->128 @40^2 now 65.9 vs 71.9 us)
+    else if (d->ksize == 3) halo = wout >= 40 || flat_tiles_enabled();   // maps under 40 wide: row-flat tiles (halo kernel)
     else halo = !(mtot <= 32768 && d->cout <= 128);
     variant = halo ? 2 : 1;
   }

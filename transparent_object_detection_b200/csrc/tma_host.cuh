@@ -116,6 +116,17 @@ inline CUtensorMapL2promotion l2_promotion_for(uint64_t window_bytes, uint64_t p
   return CU_TENSOR_MAP_L2_PROMOTION_NONE;
 }
 
+// Row-flat tiles for 3x3 stride-1 convs on small maps (conv_halo_tcgen05.cu); TOD_FLAT=0 keeps 16x8 patches / the per-tap
+// kernel for A/B measurements.
+inline bool flat_tiles_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TOD_FLAT");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 inline int num_sms() {
   static int sms[64] = {0};
   const int dev = current_device_index();
