@@ -84,6 +84,10 @@ typedef struct tod_conv_desc {
 #define TOD_CONV_REVERSE 2
 /* Tests / tools: keep the 16x8 pixel patches where the plan would pick row-flat tiles (both give bit-identical outputs). */
 #define TOD_CONV_PATCH_TILES 4
+/* Tests / tools: force the CTA-pair kernel (tcgen05 cta_group::2: two SMs share every weight tile) on / off where the
+ * plan would decide by itself.  Both give bit-identical outputs (same products, same accumulation order). */
+#define TOD_CONV_PAIR_ON 8
+#define TOD_CONV_PAIR_OFF 16
 
 int tod_conv2d_nhwc_bf16(const tod_conv_desc* desc, void* stream);
 

@@ -145,6 +145,36 @@ def test_flat_tiles_reverse_order_and_patch_tiles_are_bit_identical(case_def):
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize("reverse", [0, 1], ids=["fwd", "rev"])
+@pytest.mark.parametrize("case_def", CASES, ids=[c[0] for c in CASES])
+def test_cta_pair_kernel_is_bit_identical_to_single_cta(case_def, reverse):
+    """tcgen05 cta_group::2 (TOD_CONV_PAIR_ON): two CTAs share every weight tile as one M = 256 MMA.  Each output element is
+    the same sequence of products accumulated in the same order as in the single-CTA halo kernel, so the outputs must be
+    bit-identical -- for every tile geometry, an odd number of sub-tiles (the odd CTA idles), residual / upsample-add
+    operands, stride 2, both tile orders; channels outside the output window stay untouched."""
+    from tests import gpu_util as U
+    from transparent_object_detection_b200._lib import TOD_CONV_PAIR_OFF, TOD_CONV_PAIR_ON, TOD_CONV_REVERSE
+    name, B, H, W, cin, cout, k, s, opts = case_def
+    case = make_case(B, H, W, cin, cout, k, s, opts)
+    # the K chunk width fixes the accumulation order; where the two plans would pick different widths by themselves (the
+    # pair's half-size weight slots fit 64-channel chunks, the single CTA's do not) it is pinned for both
+    bk = {"3x3s2_c256_n512": 32}.get(name, 0)
+    outs = []
+    for flags in (TOD_CONV_PAIR_OFF, TOD_CONV_PAIR_ON):
+        out = torch.full_like(case["out"], 7.0)
+        U.run_conv(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], out, case["out_off"], case["stride"],
+                   case["act"], case["res"], case["res_off"], case["up"], bk, case["stages"], variant=2, m=case["m"],
+                   no_station=case["no_station"], flags=flags | (TOD_CONV_REVERSE if reverse else 0))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    got = outs[1][..., case["out_off"]:case["out_off"] + cout].float()
+    want = U.conv_reference(case["x"], case["x_off"], case["cin"], case["w"], case["bias"], case["stride"], case["act"],
+                            case["res"], case["res_off"], case["up"])
+    f32 = bool(opts.get("f32"))
+    rep = U.error_report(got, want, name, 2e-3 if f32 else 2e-2, 2e-3 if f32 else 2e-2)
+    assert rep["bad_frac"] == 0 and rep["nan"] == 0, rep
+
+
 def test_conv_rejects_bad_arguments():
     import ctypes as C
     from transparent_object_detection_b200 import _lib

@@ -40,6 +40,11 @@ VARIANTS = {
     "halo_n64_m1": dict(variant=2, ncap=64, m=1),
     "halo_ring_m1": dict(variant=2, no_station=1, m=1),
     "halo_ring_m2": dict(variant=2, no_station=1, m=2),
+    "pair": dict(variant=2, pair=1),             # tcgen05 cta_group::2 (TOD_CONV_PAIR_ON)
+    "pair_m1": dict(variant=2, pair=1, m=1),
+    "pair_n128": dict(variant=2, pair=1, ncap=128),
+    "pair_ring": dict(variant=2, pair=1, no_station=1),
+    "nopair": dict(variant=2, pair=-1),
     "halo_noact": dict(variant=2, act=0),        # timing experiments only (results differ by construction)
     "halo_nores": dict(variant=2, nores=1),
 }
@@ -53,6 +58,8 @@ def clone_desc(d: ConvDesc, **kw) -> ConvDesc:
     n.reserved[2] = kw.get("no_station", 0)
     n.reserved[3] = kw.get("ncap", 0)
     n.num_stages = kw.get("stages", 0)
+    if kw.get("pair"):
+        n.flags = (n.flags & ~24) | (8 if kw["pair"] > 0 else 16)
     if "bk" in kw:
         n.block_k = kw["bk"]
     if "act" in kw:

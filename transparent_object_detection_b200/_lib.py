@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
 
 
 TOD_CONV_DYNAMIC_W, TOD_CONV_REVERSE, TOD_CONV_PATCH_TILES = 1, 2, 4
+TOD_CONV_PAIR_ON, TOD_CONV_PAIR_OFF = 8, 16
 
 
 class DecodeDesc(C.Structure):

@@ -78,7 +78,11 @@ struct __align__(64) HaloParams {
   FastDiv fd_patch_cols;
   FastDiv fd_tiles_per_img, fd_tiles_w, fd_wout, fd_hw;
   long long mtot;            // batch * hout * wout
+  int batch;
   int num_subtiles, m, num_super;
+  int num_units;             // scheduled units: sub-tiles, or PAIRS of adjacent sub-tiles (2u, 2u + 1) in CTA-pair mode
+  int oob_row;               // flat 1x1 mode: a first row >= mtot (what the odd CTA of a pair loads when it has no sub-tile)
+  uint32_t b_half_rows;      // CTA-pair mode: weight rows per CTA (block_n / 2)
   int reverse;               // TOD_CONV_REVERSE: sub-tile s stands for sub-tile num_subtiles - 1 - s (last image first)
   int nowait;                // experiment: skip the programmatic-launch wait (TOD_PDL_NOWAIT=1; results are wrong)
   int dyn_w;                 // TOD_CONV_DYNAMIC_W: the weights are an earlier kernel's output (no prefetch before pdl_wait)
@@ -295,7 +299,14 @@ __device__ __forceinline__ void wait_set(const uint32_t (&bars)[4], const uint32
   }
 }
 
-template <bool SILU, bool OUT_F32, int EXTRA>
+// PAIR: the two CTAs of a (2,1,1) cluster work on adjacent sub-tiles as ONE M = 256 MMA (tcgen05 cta_group::2): each CTA
+// loads its own activation patches and only HALF of every weight tile (rows [block_n/2 r, +block_n/2)), so the weight
+// bytes an SM pulls out of L2 per output pixel halve -- the layers that stream their weights (3x3 with >= 128 channels,
+// stride 2, 20x20 maps) run at the chip's L2 -> SM limit otherwise (ncu: 38-48 B/clk/SM of xbar2l1tex reads).  The
+// leader (rank 0) issues every MMA; both producers signal the leader's "full" barriers; the leader's commits arrive on
+// the "empty" / "accumulator full" barriers of both CTAs; both CTAs' epilogue warps arrive on the leader's "accumulator
+// empty" barrier.  Primitives checked by tools/probe_pair.cu.
+template <bool SILU, bool OUT_F32, int EXTRA, bool PAIR = false>
 __global__ void __launch_bounds__((EXTRA == 7 || EXTRA == 8) ? kHaloThreadsTail : kHaloThreads, 1)
 conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -308,6 +319,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   // W2 . y + b2 straight into the NMS box candidates like EXTRA 3.  (Tail-only shared memory: static + dynamic of the
   // other variants already sits 252 bytes under the 227 KB limit.)
   constexpr bool TAIL = EXTRA == 7 || EXTRA == 8;
+  static_assert(!PAIR || EXTRA == 0 || EXTRA == 1 || EXTRA == 5 || EXTRA == 6, "CTA-pair mode: plain / residual / upsample-add convs only");
   __shared__ __align__(16) float bias2_s[TAIL ? 64 : 4];
   __shared__ __align__(8) uint64_t tail_bars[TAIL ? 5 : 1];   // tail weights landed / panel ready x2 / tail done x2
   uint64_t& w2_full_bar = tail_bars[0];
@@ -325,9 +337,32 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   // persistent schedule: this CTA owns N tile `nt`.  Full rounds are interleaved (CTA g takes super-tile r * G + g, so
   // the grid streams through adjacent memory together); what is left after the last full round is split evenly at
   // SUB-tile granularity, so the tail imbalance is one sub-tile instead of one super-tile of m.
-  const int nt = blockIdx.x % p.n_tiles;
-  const TileSched sched(p.num_subtiles, p.m, gridDim.x / p.n_tiles, blockIdx.x / p.n_tiles);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // CTA-pair mode: 0 = leader
+  const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int nt = cta % p.n_tiles;
+  const TileSched sched(p.num_units, p.m, ncta / p.n_tiles, cta / p.n_tiles);
   const int n0 = nt * p.block_n;
+  // TMA coordinates of the sub-tile this CTA takes of scheduled unit u; false (and coordinates wholly outside the tensor:
+  // loads deliver zeros, stores are clipped away) when the odd CTA of a pair has no sub-tile left
+  auto tile_coords = [&](int u, int& c1, int& c2, int& c3) -> bool {
+    int s = PAIR ? 2 * u + static_cast<int>(rank) : u;
+    if (p.reverse) s = p.num_subtiles - 1 - s;
+    const bool valid = !PAIR || static_cast<unsigned>(s) < static_cast<unsigned>(p.num_subtiles);
+    if (p.patch_mode) {
+      const int img = p.fd_tiles_per_img.div(valid ? s : 0);
+      const int rem = s - img * p.tiles_per_img;
+      const int ti = p.fd_tiles_w.div(valid ? rem : 0);
+      c1 = valid ? (rem - ti * p.tiles_w) * p.tile_w_step : 0;
+      c2 = valid ? ti * p.tile_h_step : 0;
+      c3 = valid ? img : p.batch;
+    } else {
+      c1 = valid ? s * 128 : p.oob_row;
+      c2 = 0;
+      c3 = 0;
+    }
+    return valid;
+  };
   const int acc_cols = p.m * p.block_n;   // TMEM columns of one accumulator stage
   const uint32_t a_full0 = smem_u32(&a_full[0]), a_empty0 = smem_u32(&a_empty[0]);
   const uint32_t b_full0 = smem_u32(&b_full[0]), b_empty0 = smem_u32(&b_empty[0]);   // barrier i lives at base + 8 * i
@@ -346,7 +381,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);
+      mbar_init(&tmem_empty_bar[a], PAIR ? 8 : 4);   // the leader's barrier collects both CTAs' epilogue warps
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_full_bar[a], 1);
     if (TAIL) {
@@ -359,8 +394,13 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_smem, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(&tmem_base_smem, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tmem_base_smem, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.block_n; i += kHaloThreads - 64)
@@ -370,6 +410,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything can signal them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   if (threadIdx.x == 0) pdl_launch_dependents();   // the next kernel's prologue may overlap this grid's tail
@@ -379,15 +420,19 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     if (elect_one()) {
       WaitClock wc(p.prof != nullptr);
       const long long role_t0 = wc.begin();
+      // CTA-pair mode: this CTA's half of the weight tile / its own activation patches go to its own shared memory, the
+      // bytes are counted on the LEADER's barrier, which the leader arms for both CTAs
+      const int w_row0 = n0 + (PAIR ? static_cast<int>(rank * p.b_half_rows) : 0);
+      auto load_w = [&](int i, int k) {   // weight tile of (tap, chunk) k-offset `k` into ring / resident slot i
+        if (!PAIR || rank == 0) mbar_arrive_expect_tx(&b_full[i], PAIR ? 2 * p.b_tx_bytes : p.b_tx_bytes);
+        if (PAIR) tma_load_2d_pair(&p.tm_w, pair_leader_addr(b_full0 + 8 * i), smem_base + p.off_b + i * p.b_slot_bytes, k, w_row0);
+        else tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, k, w_row0);
+      };
       auto load_resident_weights = [&]() {
 #pragma unroll 1
         for (int c = 0; c < p.chunks; ++c)
 #pragma unroll 1
-          for (int t = 0; t < p.num_taps; ++t) {
-            const int i = c * p.num_taps + t;
-            mbar_arrive_expect_tx(&b_full[i], p.b_tx_bytes);
-            tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, (t * p.chunks + c) * p.block_k, n0);
-          }
+          for (int t = 0; t < p.num_taps; ++t) load_w(c * p.num_taps + t, (t * p.chunks + c) * p.block_k);
       };
       // constant weights do not depend on earlier kernels: requested before the programmatic-launch wait
       if (p.stationary && !p.dyn_w) load_resident_weights();
@@ -413,28 +458,21 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
           long long tw = wc.begin();
           wait_addr(a_empty0 + 8 * ai, pha ^ 1u);
           wc.end(1, tw);
-          mbar_arrive_expect_tx(&a_full[ai], m_cur * p.a_tx_bytes);
+          if (!PAIR || rank == 0) mbar_arrive_expect_tx(&a_full[ai], (PAIR ? 2 : 1) * m_cur * p.a_tx_bytes);
           const uint32_t slot = smem_base + ai * p.a_slot_bytes;
 #pragma unroll 1
           for (int mt = 0; mt < m_cur; ++mt) {
-            const int s = p.reverse ? p.num_subtiles - 1 - (s0 + mt) : s0 + mt;
             int c1, c2, c3;
-            if (p.patch_mode) {
-              const int img = p.fd_tiles_per_img.div(s);
-              const int rem = s - img * p.tiles_per_img;
-              const int ti = p.fd_tiles_w.div(rem);
-              c1 = (rem - ti * p.tiles_w) * p.tile_w_step;
-              c2 = ti * p.tile_h_step;
-              c3 = img;
-            } else {
-              c1 = s * 128;
-              c2 = 0;
-              c3 = 0;
-            }
+            tile_coords(s0 + mt, c1, c2, c3);
 #pragma unroll 1
-            for (int a = 0; a < p.n_aloads; ++a)
-              tma_load_4d(&p.tm_a[p.al_map[a]], &a_full[ai], slot + mt * p.sub_bytes + p.al_off[a], c * p.block_k,
-                          c1 + p.al_dw[a], c2 + p.al_dh[a], c3);
+            for (int a = 0; a < p.n_aloads; ++a) {
+              if (PAIR)
+                tma_load_4d_pair(&p.tm_a[p.al_map[a]], pair_leader_addr(a_full0 + 8 * ai), slot + mt * p.sub_bytes + p.al_off[a],
+                                 c * p.block_k, c1 + p.al_dw[a], c2 + p.al_dh[a], c3);
+              else
+                tma_load_4d(&p.tm_a[p.al_map[a]], &a_full[ai], slot + mt * p.sub_bytes + p.al_off[a], c * p.block_k,
+                            c1 + p.al_dw[a], c2 + p.al_dh[a], c3);
+            }
           }
           if (!p.stationary) {
 #pragma unroll 1
@@ -442,9 +480,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
               tw = wc.begin();
               wait_addr(b_empty0 + 8 * bi, phb ^ 1u);
               wc.end(2, tw);
-              mbar_arrive_expect_tx(&b_full[bi], p.b_tx_bytes);
-              tma_load_2d(&p.tm_w, &b_full[bi], smem_base + p.off_b + bi * p.b_slot_bytes,
-                          (t * p.chunks + c) * p.block_k, n0);
+              load_w(bi, (t * p.chunks + c) * p.block_k);
               if (++bi == p.sb) {
                 bi = 0;
                 phb ^= 1u;
@@ -467,7 +503,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     // (waits and issue).  Warp-level waits + elect + __syncwarp around every tap group cost ~430 cycles per group in
     // which the 8-deep MMA queue (<= 512 tensor cycles at N = 128) drained: the tensor pipe was busy 66 % on the
     // weight-streaming layers.
-    if (elect_one()) {
+    if ((!PAIR || rank == 0) && elect_one()) {
     WaitClock wc(p.prof != nullptr);
     const long long role_t0 = wc.begin();
     // The whole role is instantiated per K-step count (4 / 2 / generic) and the sub-tile loop is unrolled (m <= 4): at
@@ -475,6 +511,10 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     // branch tests, loop control) that the rolled version spent per 2-MMA call made the issuing thread the limiter
     // (measured with tools/conv_profile.py: the role was busy issuing 92 % of a 32->32 3x3 layer at ~85 cycles per MMA
     // against the 40-cycle tensor floor of profiles/r1_probe_umma_rate.txt).
+    auto commit = [&](uint32_t bar_addr) {   // CTA-pair mode: the barrier at this offset in BOTH CTAs
+      if (PAIR) umma2_commit_both(bar_addr);
+      else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+    };
     auto run = [&](auto ksc) {
     constexpr int KS = decltype(ksc)::value;
     uint32_t lt = 0;
@@ -545,22 +585,26 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
                 const uint32_t d_t = tmem_acc + mt * block_n;
                 const uint32_t al = a_lo + mt * sub16;
                 if (KS == 4) {
-                  umma_bf16_k4(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
+                  if (PAIR) umma2_bf16_k4(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
+                  else umma_bf16_k4(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
                 } else if (KS == 2) {   // 32-channel chunks
-                  umma_bf16_k2(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
+                  if (PAIR) umma2_bf16_k2(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
+                  else umma_bf16_k2(d_t, al, hi_a, b_lo, hi_b, idesc, accf);
                 } else {
 #pragma unroll 1
-                  for (int k = 0; k < p.ksteps; ++k)
-                    umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, hi_b, idesc, accf | (k != 0 ? 1u : 0u));
+                  for (int k = 0; k < p.ksteps; ++k) {
+                    if (PAIR) umma2_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, hi_b, idesc, accf | (k != 0 ? 1u : 0u));
+                    else umma_bf16_k1(d_t, al + 2 * k, hi_a, b_lo + 2 * k, hi_b, idesc, accf | (k != 0 ? 1u : 0u));
+                  }
                 }
               }
             }
-            if (!p.stationary) umma_commit(&b_empty[slot0 + j]);
+            if (!p.stationary) commit(b_empty0 + 8 * (slot0 + j));
             b_lo += b_step;
           }
           if (T0 + GSZ >= p.num_taps) {
-            umma_commit(&a_empty[ai]);
-            if (c == p.chunks - 1) umma_commit(&tmem_full_bar[acc]);
+            commit(a_empty0 + 8 * ai);
+            if (c == p.chunks - 1) commit(smem_u32(&tmem_full_bar[acc]));
           }
         };
         using std::integral_constant;
@@ -765,19 +809,14 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       }
     } else {
     // tile coordinates of sub-tile s and this thread's row of the extra operand (null: row outside the tensor)
-    auto locate = [&](int s_sched, int& c1, int& c2, int& c3, const void*& ex_row) {
+    auto locate = [&](int s_sched, int& c1, int& c2, int& c3, const void*& ex_row) -> bool {
       ex_row = nullptr;
-      const int s = p.reverse ? p.num_subtiles - 1 - s_sched : s_sched;
+      const bool tile_valid = tile_coords(s_sched, c1, c2, c3);
       if (p.patch_mode) {
-        const int img = p.fd_tiles_per_img.div(s);
-        const int rem = s - img * p.tiles_per_img;
-        const int ti = p.fd_tiles_w.div(rem);
-        c1 = (rem - ti * p.tiles_w) * p.tile_w_step;
-        c2 = ti * p.tile_h_step;
-        c3 = img;
+        const int img = c3;
         if (EXTRA == 1 || EXTRA == 2) {
           const int h = c2 + rh, w = c1 + rw;
-          if (r_valid && h < p.hout && w < p.wout) {
+          if (tile_valid && r_valid && h < p.hout && w < p.wout) {
             if (EXTRA == 1)
               ex_row = p.residual + ((static_cast<long long>(img) * p.hout + h) * p.wout + w) * p.res_pitch + n0;
             else
@@ -785,12 +824,9 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
           }
         }
       } else {
-        c1 = s * 128;
-        c2 = 0;
-        c3 = 0;
         if (EXTRA == 1 || EXTRA == 2) {
-          const long long pix = static_cast<long long>(s) * 128 + r;
-          if (pix < p.mtot) {
+          const long long pix = static_cast<long long>(c1) + r;
+          if (tile_valid && pix < p.mtot) {
             if (EXTRA == 1) {
               ex_row = p.residual + pix * p.res_pitch + n0;
             } else {   // only the upsample-add needs (img, h, w) of a flat pixel index
@@ -804,6 +840,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
           }
         }
       }
+      return tile_valid;
     };
     // The extra operand was written by an earlier kernel and its first chunk is requested BEFORE the accumulator wait
     // (the loads do not depend on this grid's MMAs), so these threads order themselves after the earlier grids directly.
@@ -854,7 +891,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       int nc1 = 0, nc2 = 0, nc3 = 0;
       const void* nrow = nullptr;
       ExtraRegs<MX> exn;                     // first chunk of the coming sub-tile's extra operand
-      locate(s0, nc1, nc2, nc3, nrow);
+      bool nvalid = locate(s0, nc1, nc2, nc3, nrow);
       if (EXTRA != 0 && !RING && nrow != nullptr) exn.load(nrow, 0, first_cols);
       long long tw = wc.begin();
       wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
@@ -864,6 +901,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
 #pragma unroll 1
       for (int mt = 0; mt < m_cur; ++mt) {
         const int c1 = nc1, c2 = nc2, c3 = nc3;
+        const bool tile_valid = nvalid;     // false: the odd CTA of a pair past the last sub-tile (nothing to store)
         const void* ex_row = nrow;
         const bool ex_valid = ex_row != nullptr;
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
@@ -871,7 +909,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         ex[0] = exn;
         bool ex0_ready = true;              // ex[0] already holds the first chunk of the coming panel
         if (mt + 1 < m_cur) {               // request the next sub-tile's first chunk a whole sub-tile ahead
-          locate(s0 + mt + 1, nc1, nc2, nc3, nrow);
+          nvalid = locate(s0 + mt + 1, nc1, nc2, nc3, nrow);
           if (EXTRA != 0 && !RING && nrow != nullptr) exn.load(nrow, 0, first_cols);
         }
 #pragma unroll 1
@@ -938,7 +976,10 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
             // last TMEM read of this accumulator stage: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[group]), 0);   // the leader's MMA issuer owns both halves
+              else mbar_arrive(&tmem_empty_bar[group]);
+            }
           }
           // the previous panel's TMA store must have finished reading the staging buffer
           tw = wc.begin();
@@ -1015,7 +1056,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
           }
-          if (EXTRA != 8 && leader) {
+          if (EXTRA != 8 && leader && tile_valid) {
             tma_store_4d(&p.tm_out, stage, n0 + col0, c1, c2, c3);
             bulk_commit_group();
           }
@@ -1032,9 +1073,11 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA of a pair leaves while the other may still signal its barriers / read its operands
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
   if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1]);
 }
@@ -1052,7 +1095,7 @@ static uint32_t desc_hi(uint32_t sbo_bytes, int bk) {
 // res_ring: 0 none, 1 bf16 residual panels, 2 f32 upsample-add panels (1x1 conv on 16x8 pixel tiles) through the
 // shared-memory TMA ring of the epilogue groups.
 static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams& p, size_t* smem_bytes, bool* fits,
-                        int res_ring = 0, bool tail = false, double* cost_out = nullptr) {
+                        int res_ring = 0, bool tail = false, double* cost_out = nullptr, bool pair = false) {
   int rc;
   *fits = true;
   memset(&p, 0, sizeof(p));
@@ -1070,6 +1113,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.hout = hout;
   p.wout = wout;
   p.mtot = mtot;
+  p.batch = d->batch;
   p.cout = d->cout;
   p.block_k = bk;
   p.ksteps = bk >> 4;
@@ -1078,11 +1122,15 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   const int n_cap = (d->reserved[3] >= 16 && d->reserved[3] <= 256) ? d->reserved[3] : 256;   // tools: cap on the N tile
   p.n_tiles = ceil_div(d->cout, n_cap);
   p.block_n = round_up(ceil_div(d->cout, p.n_tiles), 16);
-  p.b_tx_bytes = p.block_n * rb;
-  p.b_slot_bytes = round_up(p.block_n * rb, 1024);
+  // CTA-pair mode: each CTA of the pair holds (and loads) half of the rows of every weight tile
+  p.b_half_rows = p.block_n / 2;
+  const int b_rows = pair ? p.block_n / 2 : p.block_n;
+  p.b_tx_bytes = b_rows * rb;
+  p.b_slot_bytes = round_up(b_rows * rb, 1024);
   p.hi_b = desc_hi(8 * rb, bk);
 
-  TOD_CHECK_ARG(mtot < (1ll << 31), "conv: too many output pixels");
+  TOD_CHECK_ARG(mtot < (1ll << 31) - 256, "conv: too many output pixels");
+  p.oob_row = static_cast<int>((mtot + 127) / 128 * 128);
   // ---- A operand: tensor maps, loads per (sub-tile, chunk), per-tap descriptor views
   uint32_t sub_bytes = 0;
   if (d->ksize == 1 && res_ring != 2) {
@@ -1220,6 +1268,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
     }
   }
   p.sub_bytes = round_up(sub_bytes, 1024);
+  p.num_units = pair ? (p.num_subtiles + 1) / 2 : p.num_subtiles;
   {
     auto make_fd = [](long long dd, long long nmax, FastDiv* f) {
       f->d = static_cast<uint32_t>(dd);
@@ -1236,7 +1285,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(k_total), static_cast<uint64_t>(d->cout)};
     const uint64_t str[1] = {static_cast<uint64_t>(k_total) * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(p.block_n)};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(b_rows)};
     if ((rc = encode_map(&p.tm_w, d->d_w, 2, dims, str, box, swz_in)) != TOD_OK) return rc;
   }
 
@@ -1318,7 +1367,7 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   int m_max = (512 - (tail ? 128 : 0)) / (2 * p.block_n);   // tail: 2 x 64 TMEM columns for the second accumulators
   if (m_max > 4) m_max = 4;
   if (m_max < 1) m_max = 1;
-  if (m_max > p.num_subtiles) m_max = p.num_subtiles;
+  if (m_max > p.num_units) m_max = p.num_units;
   if (res_ring == 1 && m_max > 2) m_max = 2;   // measured (32->32 3x3 @160^2 + residual): m = 2 91 us, m = 4 101 us
   if (d->reserved[1] > 0 && d->reserved[1] < m_max) m_max = d->reserved[1];
   double best_cost = -1.0;
@@ -1380,9 +1429,9 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
   p.off_w2 = p.off_stage + (res_ring ? 6 : 2) * kStageBytes;
   const size_t smem = static_cast<size_t>(p.off_stage) + staging + 1024;   // staging includes the residual ring
   TOD_CHECK_ARG(smem <= kHaloSmemLimit - (tail ? 1024u : 0u), "conv: shared-memory plan overflows (%zu bytes)", smem);
-  p.num_super = ceil_div(p.num_subtiles, p.m);
+  p.num_super = ceil_div(p.num_units, p.m);
 
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.block_n >> 3) << 17) | (((pair ? 256u : 128u) >> 4) << 24);
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * p.m * p.block_n + (tail ? 128 : 0))) cols <<= 1;
   p.tmem_cols = cols;
@@ -1410,6 +1459,19 @@ static int build_params(const tod_conv_desc* d, int bk, int cin_pad, HaloParams&
 // the shared-memory TMA ring; [11] bf16 out, SiLU, upsample-add through the ring; [12] bf16 out, SiLU, fused 1x1 tail
 using HaloKernel = void (*)(HaloParams);
 constexpr int kHaloVariants = 14;
+// CTA-pair instantiations of the variants that stream weights: [0] / [3] plain, [4] residual (registers), [6] f32 out,
+// [10] residual through the ring, [11] upsample-add through the ring
+static HaloKernel halo_kernel_pair(int i) {
+  switch (i) {
+    case 0: return conv_halo_tcgen05<false, false, 0, true>;
+    case 3: return conv_halo_tcgen05<true, false, 0, true>;
+    case 4: return conv_halo_tcgen05<true, false, 1, true>;
+    case 6: return conv_halo_tcgen05<false, true, 0, true>;
+    case 10: return conv_halo_tcgen05<true, false, 5, true>;
+    case 11: return conv_halo_tcgen05<true, false, 6, true>;
+    default: return nullptr;
+  }
+}
 static HaloKernel halo_kernel(int i) {
   switch (i) {
     case 0: return conv_halo_tcgen05<false, false, 0>;
@@ -1429,14 +1491,25 @@ static HaloKernel halo_kernel(int i) {
   }
 }
 
+// Where the plan uses CTA pairs by itself (measured per layer class: profiles/r2_pair_*.txt).
+static bool pair_rule(const tod_conv_desc* d) {
+  (void)d;
+  return false;
+}
+
 int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_desc* fuse) {
   static PerDeviceOnce attr_once;   // the attribute is per device
   int rc;
   if (attr_once.needed()) {
-    for (int i = 0; i < kHaloVariants - 2; ++i)   // (the tail variants set their own, smaller limit)
+    for (int i = 0; i < kHaloVariants - 2; ++i) {   // (the tail variants set their own, smaller limit)
       if ((rc = check_cuda(cudaFuncSetAttribute(halo_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit),
                            "cudaFuncSetAttribute(conv_halo_tcgen05)")) != TOD_OK)
         return rc;
+      if (halo_kernel_pair(i) != nullptr &&
+          (rc = check_cuda(cudaFuncSetAttribute(halo_kernel_pair(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemLimit),
+                           "cudaFuncSetAttribute(conv_halo_tcgen05 pair)")) != TOD_OK)
+        return rc;
+    }
     attr_once.done();
   }
   const bool silu = d->act == TOD_ACT_SILU, f32 = d->out_dtype == TOD_OUT_F32;
@@ -1459,6 +1532,14 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
     kvar = fuse->mode == TOD_FUSE_BOX ? 8 : 9;
   }
 
+  // CTA pairs (cta_group::2): forced by the descriptor (tools / tests), else by the plan's rule -- the layers whose weight
+  // stream is what bounds them: 3x3 convs with >= 128 output channels (every stride) and 1x1 convs that cannot keep
+  // their weights resident
+  bool pair = false;
+  if (fuse == nullptr && !(d->flags & TOD_CONV_PAIR_OFF) && pair_mode() != 0 && num_sms() >= 2) {
+    if ((d->flags & TOD_CONV_PAIR_ON) || pair_mode() == 2) pair = true;
+    else pair = pair_rule(d);
+  }
   HaloParams p;
   size_t smem = 0;
   bool fits = false;
@@ -1466,17 +1547,21 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
   const int cin_pad = round_up(d->cin, bk0);
   if (extra == 1 && silu && fuse == nullptr && d->reserved[2] != 1) {
     // residual through the shared-memory TMA ring when the weights can stay resident next to it
-    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 1)) != TOD_OK) return rc;
+    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 1, false, nullptr, pair)) != TOD_OK) return rc;
     if (fits) kvar = 10;
   }
   if (extra == 2 && silu && fuse == nullptr && d->ksize == 1 && d->stride == 1 && d->cout % 64 == 0 && d->reserved[2] != 1) {
     // upsample-add operand through the ring (1x1 conv on pixel tiles)
-    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 2)) != TOD_OK) return rc;
+    if ((rc = build_params(d, bk0, cin_pad, p, &smem, &fits, 2, false, nullptr, pair)) != TOD_OK) return rc;
     if (fits) kvar = 11;
+  }
+  if (pair && halo_kernel_pair(kvar) == nullptr) {   // no pair instantiation of this flavour
+    pair = false;
+    fits = false;
   }
   double cost = 0.0;
   for (int bk = bk0; bk >= 16 && !fits; bk >>= 1)
-    if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits, 0, false, &cost)) != TOD_OK) return rc;
+    if ((rc = build_params(d, bk, cin_pad, p, &smem, &fits, 0, false, &cost, pair)) != TOD_OK) return rc;
   TOD_CHECK_ARG(fits, "conv: no shared-memory plan fits (cin %d cout %d ksize %d stride %d)", d->cin, d->cout, d->ksize,
                 d->stride);
   if (kvar != 10 && kvar != 11 && fuse == nullptr && d->ksize == 3 && d->cout > 128 && d->reserved[3] == 0) {
@@ -1489,7 +1574,7 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
     size_t smem2 = 0;
     bool fits2 = false;
     double cost2 = 0.0;
-    if ((rc = build_params(&d2, p.block_k, cin_pad, p2, &smem2, &fits2, 0, false, &cost2)) != TOD_OK) return rc;
+    if ((rc = build_params(&d2, p.block_k, cin_pad, p2, &smem2, &fits2, 0, false, &cost2, pair)) != TOD_OK) return rc;
     if (fits2 && cost2 < cost * 0.9) {
       p = p2;
       smem = smem2;
@@ -1509,10 +1594,17 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
     p.cand_cls = fuse->d_cand_cls;
   }
   const long long work = static_cast<long long>(p.num_super) * p.n_tiles;
-  long long grid = num_sms();
+  long long grid = pair ? num_sms() / 2 : num_sms();   // CTAs, or CTA pairs
   if (grid > work) grid = work;
   grid -= grid % p.n_tiles;
   if (grid < p.n_tiles) grid = p.n_tiles;
+  if (pair) {
+    if ((rc = check_cuda(launch_pdl_pair(halo_kernel_pair(kvar), dim3(static_cast<unsigned>(2 * grid)), dim3(kHaloThreads), smem,
+                                         static_cast<cudaStream_t>(stream), p),
+                         "conv_halo_tcgen05 (CTA pairs) launch")) != TOD_OK)
+      return rc;
+    return TOD_OK;
+  }
   HaloKernel kern = halo_kernel(kvar);
   if ((rc = check_cuda(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kHaloThreads), smem,
                                   static_cast<cudaStream_t>(stream), p),

@@ -449,6 +449,7 @@ extern "C" int tod_conv2d_nhwc_bf16(const tod_conv_desc* d, void* stream) {
     if (d->ksize == 3 && d->stride == 2) halo = d->cin <= 32;
     else if (d->ksize == 3) halo = wout >= 40 || flat_tiles_enabled();   // maps under 40 wide: row-flat tiles (halo kernel)
     else halo = !(mtot <= 32768 && d->cout <= 128);
+    if (d->flags & TOD_CONV_PAIR_ON) halo = true;   // CTA pairs exist in the halo kernel only
     variant = halo ? 2 : 1;
   }
   if (variant == 2) return conv_halo_launch(d, stream);

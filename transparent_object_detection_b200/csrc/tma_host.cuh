@@ -95,6 +95,36 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// Same, as (2,1,1) clusters: CTA pairs for the tcgen05 cta_group::2 kernels (grid.x must be even).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_pair(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// CTA-pair conv kernels: TOD_PAIR=0 never, 2 wherever the kernel supports it, default (1) where the plan's rule says so.
+inline int pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TOD_PAIR");
+    mode = (e != nullptr) ? atoi(e) : 1;
+  }
+  return mode;
+}
+
 // L2 promotion (the granularity at which a TMA load's misses are fetched into L2) for a tensor whose innermost box covers
 // `window_bytes` of a `pitch_bytes` pixel: a channel WINDOW of a wider concat buffer (C2f's chunk / bottleneck inputs,
 // model/blocks.py:104-108) must not be promoted past its own width, or every miss drags the neighbouring windows' bytes
