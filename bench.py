@@ -60,6 +60,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.power = []              # board power in W next to every clock sample
         self.active = False          # only samples taken inside a timed region count
         try:
             import pynvml
@@ -82,6 +83,7 @@ class ClockSampler(threading.Thread):
             if self.active:
                 try:
                     self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                     for bit, name in names.items():
                         if r & bit:
@@ -94,7 +96,9 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_min_mhz": float(np.min(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_median": float(np.median(self.power)) if self.power else None,
+                "power_w_max": float(np.max(self.power)) if self.power else None}
 
 
 def bind_to_gpu_numa_node(local_rank: int):

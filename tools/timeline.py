@@ -34,7 +34,7 @@ def main():
     engs = [model.engine(a.batch, a.size, a.size, dev, instance=i) for i in range(a.plans)]
     L = engs[0].L
     cap = 1 << 20
-    buf = torch.zeros(2 + 6 * cap, dtype=torch.int64, device=dev)
+    buf = torch.zeros(2 + 8 * cap, dtype=torch.int64, device=dev)
     buf[1] = cap
     check(L.tod_debug_set_timeline(buf.data_ptr()), "set timeline")
     graphs = [e.graph_for("u8", 0, 0.05, 0.5) for e in engs]            # captured WITH the tags (the warm-up pass records too)
@@ -66,10 +66,29 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     n = int(buf[0])
-    rec = buf[2:2 + 6 * min(n, cap)].view(-1, 6).cpu().numpy()
+    rec = buf[2:2 + 8 * min(n, cap)].view(-1, 8).cpu().numpy()
     check(L.tod_debug_set_timeline(None), "clear timeline")
-    ids, sm, t0, t1 = (rec[:, 0] & 0xffffffff).astype(np.int64), rec[:, 1].astype(np.int64), rec[:, 2].astype(np.int64), rec[:, 3].astype(np.int64)
+    ids, sm, t0, t1 = (rec[:, 0] & 0xffffffff).astype(np.int64), (rec[:, 1] & 0xffff).astype(np.int64), rec[:, 2].astype(np.int64), rec[:, 3].astype(np.int64)
+    cyc_end = (rec[:, 1].astype(np.uint64) >> np.uint64(16)).astype(np.int64)          # SM cycle counter (48 bits) at CTA end
+    # SM clock under this load: consecutive CTA ends on the same SM, cycles / globaltimer ns
+    ghz = []
+    ghz_num, ghz_den = {}, {}     # per launch id: cycles / ns over the intervals that END with one of its CTAs
+    for s_ in range(int(sm.max()) + 1):
+        sel = np.nonzero(sm == s_)[0]
+        o = sel[np.argsort(t1[sel])]
+        dt, dc = np.diff(t1[o]), np.diff(cyc_end[o])
+        ok = (dt > 20000) & (dc > 0)
+        if ok.any():
+            ghz.append(float(dc[ok].sum() / dt[ok].sum()))
+        for k in np.nonzero((dt > 3000) & (dc > 0))[0]:
+            i_ = int(ids[o[k + 1]])
+            ghz_num[i_] = ghz_num.get(i_, 0) + int(dc[k])
+            ghz_den[i_] = ghz_den.get(i_, 0) + int(dt[k])
+    if ghz:
+        print(f"SM clock during the replays (cycle counter / globaltimer between CTA ends, per SM): median {np.median(ghz):.3f} GHz, "
+              f"min {min(ghz):.3f}, max {max(ghz):.3f}")
     t_ready, t_acc = rec[:, 4].astype(np.int64), rec[:, 5].astype(np.int64)
+    t_mma, t_last = rec[:, 6].astype(np.int64), rec[:, 7].astype(np.int64)
     T0, T1 = int(t0.min()), int(t1.max())
     span = T1 - T0
     n_sm = int(sm.max()) + 1
@@ -103,14 +122,20 @@ def main():
         rdy, acc = t_ready[sel], t_acc[sel]
         wait_us = float(np.where(rdy > 0, rdy - t0[sel], 0).mean() / 1e3)          # CTA start -> programmatic-launch wait returned
         fill_us = float(np.where((acc > 0) & (rdy > 0), acc - rdy, 0).mean() / 1e3)  # -> first complete accumulator
-        rows.append({"id": int(i), "name": names[i] if i < len(names) else "?", "ctas": int(sel.sum()),
+        mma_end, last = t_mma[sel], t_last[sel]
+        steady_us = float(np.where((last > 0) & (acc > 0), last - acc, 0).mean() / 1e3)      # first -> last accumulator complete
+        drain_us = float(np.where(last > 0, t1[sel] - last, 0).mean() / 1e3)                # last accumulator -> CTA end
+        mma_tail_us = float(np.where(mma_end > 0, t1[sel] - mma_end, 0).mean() / 1e3)       # MMA role done -> CTA end
+        rows.append({"steady_us": steady_us, "drain_us": drain_us, "mma_tail_us": mma_tail_us,
+                     "ghz": (ghz_num[int(i)] / ghz_den[int(i)]) if ghz_den.get(int(i)) else 0.0,
+                     "id": int(i), "name": names[i] if i < len(names) else "?", "ctas": int(sel.sum()),
                      "cta_us_mean": float(dur.mean() / 1e3), "cta_us_max": float(dur.max() / 1e3), "wait_us": wait_us, "fill_us": fill_us,
                      "sm_time_share": float(dur.sum() / total_cta_ns), "sm_us_per_step": float(dur.sum() / 1e3 / n_sm / a.replays * 1.0)})
     # one graph = one set of ids per plan; fold the plans' copies of the same layer together by name order
-    print(f"{'launch':>6s} {'kernel':40s} {'CTAs':>7s} {'us/CTA':>8s} {'max':>8s} {'pdl-wait':>9s} {'fill':>6s} {'SM-us/step':>11s} {'share':>7s}")
+    print(f"{'launch':>6s} {'kernel':40s} {'CTAs':>7s} {'us/CTA':>8s} {'max':>8s} {'pdl-wait':>9s} {'fill':>6s} {'steady':>7s} {'drain':>6s} {'GHz':>5s} {'SM-us/step':>11s} {'share':>7s}")
     for r in rows:
         print(f"{r['id']:6d} {r['name']:40s} {r['ctas']:7d} {r['cta_us_mean']:8.1f} {r['cta_us_max']:8.1f} {r['wait_us']:9.1f} {r['fill_us']:6.1f} "
-              f"{r['sm_us_per_step']:11.1f} {100 * r['sm_time_share']:6.2f}%")
+              f"{r['steady_us']:7.1f} {r['drain_us']:6.1f} {r['ghz']:5.2f} {r['sm_us_per_step']:11.1f} {100 * r['sm_time_share']:6.2f}%")
     by_name = {}
     for r in rows:
         by_name.setdefault(r["name"], 0.0)

@@ -326,13 +326,13 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   uint64_t* const p_full_bar = &tail_bars[TAIL ? 1 : 0];
   uint64_t* const d2_full_bar = &tail_bars[TAIL ? 3 : 0];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ unsigned long long tl_marks[2];   // timeline: programmatic wait returned / first accumulator complete
+  __shared__ unsigned long long tl_marks[4];   // timeline: programmatic wait returned / first accumulator complete / MMA role done / last accumulator complete
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const unsigned long long tl_t0 = (p.tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
-  if (p.tl.buf != nullptr && threadIdx.x == 0) tl_marks[0] = tl_marks[1] = 0;
+  if (p.tl.buf != nullptr && threadIdx.x == 0) tl_marks[0] = tl_marks[1] = tl_marks[2] = tl_marks[3] = 0;
 
   // persistent schedule: this CTA owns N tile `nt`.  Full rounds are interleaved (CTA g takes super-tile r * G + g, so
   // the grid streams through adjacent memory together); what is left after the last full round is split evenly at
@@ -415,27 +415,50 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   const uint32_t tmem_base = tmem_base_smem;
   if (threadIdx.x == 0) pdl_launch_dependents();   // the next kernel's prologue may overlap this grid's tail
 
+  // CTA-pair mode: this CTA's half of the weight tile / its own activation patches go to its own shared memory, the
+  // bytes are counted on the LEADER's barrier, which the leader arms for both CTAs
+  const int w_row0 = n0 + (PAIR ? static_cast<int>(rank * p.b_half_rows) : 0);
+  auto load_w = [&](int i, int k) {   // weight tile of (tap, chunk) k-offset `k` into ring / resident slot i
+    if (!PAIR || rank == 0) mbar_arrive_expect_tx(&b_full[i], PAIR ? 2 * p.b_tx_bytes : p.b_tx_bytes);
+    if (PAIR) tma_load_2d_pair(&p.tm_w, pair_leader_addr(b_full0 + 8 * i), smem_base + p.off_b + i * p.b_slot_bytes, k, w_row0);
+    else tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, k, w_row0);
+  };
+  auto load_resident_weights = [&]() {
+#pragma unroll 1
+    for (int c = 0; c < p.chunks; ++c)
+#pragma unroll 1
+      for (int t = 0; t < p.num_taps; ++t) load_w(c * p.num_taps + t, (t * p.chunks + c) * p.block_k);
+  };
+  // Streamed weights: the first pass through the ring is requested ahead of the programmatic-launch wait as well (the tile
+  // sequence of a super-tile -- chunk-major, taps inside -- repeats for every super-tile, so ring slot q holds tile q of
+  // the sequence; never more than this CTA consumes): these bytes then cross the L2 -> SM fabric while the previous grid
+  // drains instead of in the burst every CTA starts with.
+  const int b_per_tile = p.num_taps * p.chunks;
+  const long long b_wanted = static_cast<long long>(sched.iters()) * b_per_tile;
+  const int b_prefetched = (!p.stationary && !p.dyn_w) ? (b_wanted < p.sb ? static_cast<int>(b_wanted) : p.sb) : 0;
+  // Constant weights do not depend on earlier kernels.  They are requested by the MMA warp's thread (idle until the first
+  // operands land) so that the producer reaches its wait -- and the first activation loads behind it -- without first
+  // issuing up to 40 weight loads (~0.13 us each).
+  auto prefetch_weights = [&]() {
+    if (p.dyn_w) return;
+    if (p.stationary) {
+      load_resident_weights();
+      return;
+    }
+#pragma unroll 1
+    for (int q = 0; q < b_prefetched; ++q) {
+      const int qq = q % b_per_tile;
+      const int c = qq / p.num_taps, t = qq - c * p.num_taps;
+      load_w(q, (t * p.chunks + c) * p.block_k);
+    }
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected lane)
     if (elect_one()) {
       WaitClock wc(p.prof != nullptr);
       const long long role_t0 = wc.begin();
-      // CTA-pair mode: this CTA's half of the weight tile / its own activation patches go to its own shared memory, the
-      // bytes are counted on the LEADER's barrier, which the leader arms for both CTAs
-      const int w_row0 = n0 + (PAIR ? static_cast<int>(rank * p.b_half_rows) : 0);
-      auto load_w = [&](int i, int k) {   // weight tile of (tap, chunk) k-offset `k` into ring / resident slot i
-        if (!PAIR || rank == 0) mbar_arrive_expect_tx(&b_full[i], PAIR ? 2 * p.b_tx_bytes : p.b_tx_bytes);
-        if (PAIR) tma_load_2d_pair(&p.tm_w, pair_leader_addr(b_full0 + 8 * i), smem_base + p.off_b + i * p.b_slot_bytes, k, w_row0);
-        else tma_load_2d(&p.tm_w, &b_full[i], smem_base + p.off_b + i * p.b_slot_bytes, k, w_row0);
-      };
-      auto load_resident_weights = [&]() {
-#pragma unroll 1
-        for (int c = 0; c < p.chunks; ++c)
-#pragma unroll 1
-          for (int t = 0; t < p.num_taps; ++t) load_w(c * p.num_taps + t, (t * p.chunks + c) * p.block_k);
-      };
-      // constant weights do not depend on earlier kernels: requested before the programmatic-launch wait
-      if (p.stationary && !p.dyn_w) load_resident_weights();
+      int b_pre = b_prefetched;
       if (TAIL) {
         mbar_arrive_expect_tx(&w2_full_bar, 64u * 128u);
         tma_load_2d(&p.tm_w2, &w2_full_bar, smem_base + p.off_w2, 0, 0);
@@ -477,10 +500,14 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
           if (!p.stationary) {
 #pragma unroll 1
             for (int t = 0; t < p.num_taps; ++t) {
-              tw = wc.begin();
-              wait_addr(b_empty0 + 8 * bi, phb ^ 1u);
-              wc.end(2, tw);
-              load_w(bi, (t * p.chunks + c) * p.block_k);
+              if (b_pre > 0) {
+                --b_pre;             // requested before the programmatic-launch wait
+              } else {
+                tw = wc.begin();
+                wait_addr(b_empty0 + 8 * bi, phb ^ 1u);
+                wc.end(2, tw);
+                load_w(bi, (t * p.chunks + c) * p.block_k);
+              }
               if (++bi == p.sb) {
                 bi = 0;
                 phb ^= 1u;
@@ -503,7 +530,9 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     // (waits and issue).  Warp-level waits + elect + __syncwarp around every tap group cost ~430 cycles per group in
     // which the 8-deep MMA queue (<= 512 tensor cycles at N = 128) drained: the tensor pipe was busy 66 % on the
     // weight-streaming layers.
-    if ((!PAIR || rank == 0) && elect_one()) {
+    const bool mma_thread = elect_one();
+    if (mma_thread) prefetch_weights();   // (both CTAs of a pair: each its own halves)
+    if ((!PAIR || rank == 0) && mma_thread) {
     WaitClock wc(p.prof != nullptr);
     const long long role_t0 = wc.begin();
     // The whole role is instantiated per K-step count (4 / 2 / generic) and the sub-tile loop is unrolled (m <= 4): at
@@ -629,6 +658,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     if (p.ksteps == 4) run(std::integral_constant<int, 4>{});
     else if (p.ksteps == 2) run(std::integral_constant<int, 2>{});
     else run(std::integral_constant<int, 0>{});
+    if (p.tl.buf != nullptr) tl_marks[2] = global_timer_ns();
     if (wc.on) {
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
@@ -883,9 +913,16 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     }
     const uint32_t lr_off = static_cast<uint32_t>(((r >> 4) << 2) + ((r & 7) >> 1)) * 128u;   // EXTRA 6: this row's low-res row
     int rj = 0;   // panels consumed by this group
+    // The LAST accumulator of a CTA is drained by BOTH groups (alternate panels): nothing is left to overlap with, and the
+    // time from the last MMA to the CTA's exit is a tensor-pipe bubble on this SM (measured 4 us of a ~35 us CTA).
+    constexpr bool kSplitLast = EXTRA == 0;
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it, ++lt) {
-      if ((lt & 1) != static_cast<uint32_t>(group)) continue;
+      const uint32_t acc_stage = lt & 1;   // accumulator stage of this iteration (its owner is group acc_stage)
+      const bool split = kSplitLast && it == n_it - 1;
+      if (acc_stage != static_cast<uint32_t>(group) && !split) continue;
+      const uint32_t split_sel = acc_stage == static_cast<uint32_t>(group) ? 0u : 1u;   // owner: even panels, helper: odd panels
+      uint32_t item = 0;
       int s0, m_cur;
       sched.get(it, s0, m_cur);
       int nc1 = 0, nc2 = 0, nc3 = 0;
@@ -894,9 +931,13 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
       bool nvalid = locate(s0, nc1, nc2, nc3, nrow);
       if (EXTRA != 0 && !RING && nrow != nullptr) exn.load(nrow, 0, first_cols);
       long long tw = wc.begin();
-      wait_addr(smem_u32(&tmem_full_bar[group]), (lt >> 1) & 1);
+      wait_addr(smem_u32(&tmem_full_bar[acc_stage]), (lt >> 1) & 1);
       wc.end(1, tw);
-      if (p.tl.buf != nullptr && it == 0 && leader) tl_marks[1] = global_timer_ns();
+      if (p.tl.buf != nullptr && leader) {
+        const unsigned long long now = global_timer_ns();
+        if (it == 0) tl_marks[1] = now;
+        tl_marks[3] = now;   // (the two groups alternate: the later write is the later accumulator)
+      }
       tcgen05_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < m_cur; ++mt) {
@@ -904,7 +945,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         const bool tile_valid = nvalid;     // false: the odd CTA of a pair past the last sub-tile (nothing to store)
         const void* ex_row = nrow;
         const bool ex_valid = ex_row != nullptr;
-        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * acc_cols + mt * p.block_n;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * acc_cols + mt * p.block_n;
         ExtraRegs<MX> ex[kChunks];
         ex[0] = exn;
         bool ex0_ready = true;              // ex[0] already holds the first chunk of the coming panel
@@ -914,6 +955,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         }
 #pragma unroll 1
         for (int pn = 0; pn < npanels; ++pn) {
+          if (kSplitLast && split && ((item++ & 1u) != split_sel)) continue;   // the other group's panel
           const int col0 = pn * p.pc;
           const int ncols = min(p.pc, p.block_n - col0);
           if (EXTRA != 0 && !RING && ex_valid && !ex0_ready) ex[0].load(ex_row, col0, min(32, ncols));
@@ -972,13 +1014,13 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
                 epilogue_math<16, SILU, OUT_F32, MX>(v, bias_s + col0 + cc, ex[ch], ex_valid || RING, &o[ch * kWordsPerChunk]);
             }
           }
-          if (mt == m_cur - 1 && pn == npanels - 1) {
-            // last TMEM read of this accumulator stage: hand it back to the MMA warp
+          if (mt == m_cur - 1 && pn == npanels - 1 && !split) {
+            // last TMEM read of this accumulator stage: hand it back to the MMA warp (nobody waits for the CTA's last one)
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[group]), 0);   // the leader's MMA issuer owns both halves
-              else mbar_arrive(&tmem_empty_bar[group]);
+              if (PAIR) mbar_arrive_cluster(smem_u32(&tmem_empty_bar[acc_stage]), 0);   // the leader's MMA issuer owns both halves
+              else mbar_arrive(&tmem_empty_bar[acc_stage]);
             }
           }
           // the previous panel's TMA store must have finished reading the staging buffer
@@ -1063,7 +1105,9 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
         }
       }
     }
-    if (leader) bulk_wait_all();
+    // the staging buffers must outlive the stores' READS; their writes are this grid's memory operations, which grid
+    // completion (and the dependent grid's programmatic-launch wait) covers
+    if (leader) bulk_wait_read_all();
     if (wc.on) {
       wc.end(0, role_t0);
       for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 8 + group * 4 + i] = wc.acc[i];
@@ -1079,7 +1123,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
-  if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1]);
+  if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1], tl_marks[2], tl_marks[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -1491,10 +1535,13 @@ static HaloKernel halo_kernel(int i) {
   }
 }
 
-// Where the plan uses CTA pairs by itself (measured per layer class: profiles/r2_pair_*.txt).
+// Where the plan uses CTA pairs by itself.  Measured per layer at batch 64 (profiles/r2_pair_vs_single_per_layer.txt): the
+// weight stream is NOT what bounds the single-CTA kernel (xbar2l1tex reads 20-27 B/clk/SM on the 3x3 layers, half the
+// chip's L2 -> SM limit), so halving it buys nothing there and the cluster launch costs 1-2 us.  What pairs do buy is
+// shared memory: with half-size weight slots the residual layers of the 64-channel bottlenecks keep resident weights, the
+// residual ring AND two sub-tiles per weight tile (m = 2; m = 1 alone costs 33 % at N = 64): 71 -> 60 us.
 static bool pair_rule(const tod_conv_desc* d) {
-  (void)d;
-  return false;
+  return d->ksize == 3 && d->stride == 1 && d->d_residual != nullptr && d->act == TOD_ACT_SILU && d->cin == 64 && d->cout == 64;
 }
 
 int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_desc* fuse) {
