@@ -565,6 +565,13 @@ def main():
                     row["gflop"] += 2.0 * B * ho * wo * 64 * 64 / 1e9
                     row["shape"] += " + 64->64 k1 (fused tail)"
                 row["tflops"] = row["gflop"] / row["ms"]
+            elif kind == "stem":      # uint8 image in, bf16 NHWC feature map out
+                row["mbytes"] = (B * args.size * args.size * 3 + B * (args.size // 2) ** 2 * C_ * 2) / 1e6
+                row["shape"] = f"u8 3->{C_} k3 s2 @{args.size // 2}x{args.size // 2}"
+            elif kind == "pool":      # one plane read, three pooled planes written
+                buf, c_ = payload
+                row["mbytes"] = 4 * B * buf.h * buf.w * c_ * 2 / 1e6
+                row["shape"] = f"3x maxpool5 {c_}ch @{buf.h}x{buf.w}"
             table.append(row)
 
     if rank == 0:

@@ -4,11 +4,23 @@
 // pooled planes are written to channels [c,2c), [2c,3c), [3c,4c) -- no cat, no intermediate round trip.
 // HBM-bound: reads c*H*W*2 bytes, writes 3x that.  One CTA = one image x one group of CG channels; each 5x5
 // max is done separably (row pass, column pass) with 8-channel (16-byte) vectors; -inf padding == clipped windows.
-#include "tod_common.cuh"
+#include <cstdlib>
+
+#include "tma_host.cuh"
 
 namespace tod {
 
 constexpr int kPoolThreads = 256;
+
+// TOD_POOL_TMA=0: the LDG / STG kernels below instead of the TMA kernel (A/B measurements; both are exact)
+static bool pool_tma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TOD_POOL_TMA");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 __device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
   uint4 r;
@@ -131,6 +143,103 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_fast_kernel(__nv_bfloa
   if (threadIdx.x == 0) timeline_write(tl, tl_t0);
 }
 
+// TMA version (every plane of the detector at 640^2 and 1280^2).  The kernels above turned out to be bound by shared-memory
+// bandwidth, not HBM: a separable 5-tap max that re-reads its five inputs per output moves 96 bytes of shared memory per
+// 16-byte element and pass (ncu: 27 us for 52 MB = 28 % of the HBM peak).  Here one thread owns a whole row (then a whole
+// column) of one 8-channel vector and keeps the window in registers -- 1.4 shared-memory loads and one store per element
+// and pass, three packed maxima via m2[i] = max(x[i], x[i+1]), m5[i] = max(m2[i], m2[i+2], x[i+4]) -- the plane arrives
+// by ONE tensor-map load and every pooled plane leaves by one TMA store straight from the
+// buffer the next stage reads.  One CTA = one image x one group of 8 * VEC channels.
+struct PoolTma {
+  CUtensorMap tm;   // [batch, h, w, pitch] bf16, box {8 * VEC channels, w, h, 1}
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kPoolThreads) sppf_pool_tma_kernel(const __grid_constant__ PoolTma tm, int h, int w, int c,
+                                                                     const TimelineTag tl) {
+  const unsigned long long tl_t0 = (tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
+  extern __shared__ uint8_t pool_raw[];
+  __shared__ __align__(8) uint64_t full_bar;
+  const uint32_t base = (smem_u32(pool_raw) + 127u) & ~127u;
+  const int total = h * w * VEC;                       // uint4 elements of one plane
+  const uint32_t b0 = base, b1 = base + static_cast<uint32_t>(total) * 16u;
+  const int groups = c / (8 * VEC);
+  const int n = blockIdx.x / groups;
+  const int c0 = (blockIdx.x - n * groups) * 8 * VEC;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.tm);
+    mbar_init(&full_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&full_bar, static_cast<uint32_t>(total) * 16u);
+    tma_load_4d(&tm.tm, &full_bar, b0, c0, 0, 0, n);
+  }
+  mbar_wait(&full_bar, 0);
+  auto lds = [](uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+  };
+  auto sts = [](uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  };
+  // one pass along a line of `len` elements `stride` bytes apart: out[i] = max(in[i-2 .. i+2]) clipped to the line (a
+  // clipped window == the reference's implicit -inf padding, model/blocks.py:135; a repeated edge element is harmless
+  // under max).  Ten outputs per step from fourteen loads issued together: the loads of a step are independent, so the
+  // shared-memory latency is paid once per step instead of once per element.
+  auto line_pass = [&](uint32_t src, uint32_t dst, int len, uint32_t stride) {
+    constexpr int CH = 10;
+#pragma unroll 1
+    for (int base_i = 0; base_i < len; base_i += CH) {
+      uint4 x[CH + 4];
+#pragma unroll
+      for (int j = 0; j < CH + 4; ++j) {
+        const int idx = min(max(base_i + j - 2, 0), len - 1);
+        x[j] = lds(src + static_cast<uint32_t>(idx) * stride);
+      }
+      uint4 m2[CH + 3];
+#pragma unroll
+      for (int j = 0; j < CH + 3; ++j) m2[j] = max_bf16x8(x[j], x[j + 1]);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (base_i + j < len) {
+          const uint4 m = max_bf16x8(max_bf16x8(m2[j], m2[j + 2]), x[j + 4]);
+          sts(dst + static_cast<uint32_t>(base_i + j) * stride, m);
+        }
+      }
+    }
+  };
+  const uint32_t px_bytes = VEC * 16u, row_bytes = static_cast<uint32_t>(w) * px_bytes;
+#pragma unroll 1
+  for (int stage = 1; stage <= 3; ++stage) {
+    // row pass b0 -> b1: task = (row y, vector v)
+    for (int tsk = threadIdx.x; tsk < h * VEC; tsk += kPoolThreads) {
+      const int y = tsk / VEC, v = tsk - y * VEC;
+      const uint32_t off = static_cast<uint32_t>(y) * row_bytes + v * 16u;
+      line_pass(b0 + off, b1 + off, w, px_bytes);
+    }
+    if (threadIdx.x == 0) bulk_wait_read_all();   // the previous stage's store has finished reading b0
+    __syncthreads();
+    // column pass b1 -> b0: task = (column x, vector v)
+    for (int tsk = threadIdx.x; tsk < w * VEC; tsk += kPoolThreads) {
+      const uint32_t off = static_cast<uint32_t>(tsk) * 16u;   // (x * VEC + v) * 16
+      line_pass(b1 + off, b0 + off, h, row_bytes);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {   // pooled plane `stage` -> channel slot `stage` of the concat buffer
+      tma_store_4d(&tm.tm, b0, stage * c + c0, 0, 0, n);
+      bulk_commit_group();
+    }
+  }
+  if (threadIdx.x == 0) {
+    bulk_wait_read_all();
+    timeline_write(tl, tl_t0);
+  }
+}
+
 }  // namespace tod
 
 using namespace tod;
@@ -153,6 +262,47 @@ extern "C" int tod_sppf_pool_nhwc_bf16(void* d_buf, int32_t batch, int32_t h, in
   }
   const size_t plane16 = static_cast<size_t>(h) * w * 16;  // bytes for one 8-channel vector plane
   auto st = static_cast<cudaStream_t>(stream);
+  // TMA path: the widest channel group whose two plane buffers stay under ~100 KB (two CTAs per SM)
+  if (pool_tma_enabled() && h <= 256 && w <= 256 && h >= 3 && w >= 3) {
+    int vec = 0;
+    static int vec_cap = -1;   // TOD_POOL_VEC: cap on the channel-group width (tools)
+    if (vec_cap < 0) {
+      const char* e = getenv("TOD_POOL_VEC");
+      vec_cap = e != nullptr ? atoi(e) : 8;
+    }
+    for (int v : {8, 4, 2})
+      if (v <= vec_cap && c % (8 * v) == 0 && 2 * plane16 * v + 256 <= 104 * 1024) {
+        vec = v;
+        break;
+      }
+    if (vec != 0) {
+      PoolTma tm;
+      const uint64_t px = static_cast<uint64_t>(pitch) * 2;
+      const uint64_t dims[4] = {static_cast<uint64_t>(pitch), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                                static_cast<uint64_t>(batch)};
+      const uint64_t str[3] = {px, px * w, px * w * h};
+      const uint32_t box[4] = {static_cast<uint32_t>(8 * vec), static_cast<uint32_t>(w), static_cast<uint32_t>(h), 1};
+      int rc = encode_map(&tm.tm, d_buf, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE);
+      if (rc != TOD_OK) return rc;
+      const size_t smem = 2 * plane16 * vec + 256;
+      const unsigned grid = static_cast<unsigned>(batch) * (c / (8 * vec));
+      static PerDeviceOnce tma_attr_once;
+      if (tma_attr_once.needed()) {
+        rc = check_cuda(cudaFuncSetAttribute(sppf_pool_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "attr pool<8>");
+        if (rc == TOD_OK) rc = check_cuda(cudaFuncSetAttribute(sppf_pool_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "attr pool<4>");
+        if (rc == TOD_OK) rc = check_cuda(cudaFuncSetAttribute(sppf_pool_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "attr pool<2>");
+        if (rc != TOD_OK) return rc;
+        tma_attr_once.done();
+      }
+      const TimelineTag tag = timeline_tag("sppf pool");
+      if (vec == 8) sppf_pool_tma_kernel<8><<<grid, kPoolThreads, smem, st>>>(tm, h, w, c, tag);
+      else if (vec == 4) sppf_pool_tma_kernel<4><<<grid, kPoolThreads, smem, st>>>(tm, h, w, c, tag);
+      else sppf_pool_tma_kernel<2><<<grid, kPoolThreads, smem, st>>>(tm, h, w, c, tag);
+      TOD_CHECK_LAUNCH("sppf_pool_tma_kernel launch");
+      return TOD_OK;
+    }
+  }
   if (c % 16 == 0 && h * w * 2 <= kFastElems * kPoolThreads) {
     sppf_pool_fast_kernel<2><<<batch * (c / 16), kPoolThreads, 2 * 2 * plane16, st>>>(
         reinterpret_cast<__nv_bfloat16*>(d_buf), h, w, c, pitch, timeline_tag("sppf pool"));
