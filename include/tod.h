@@ -89,6 +89,16 @@ typedef struct tod_conv_desc {
 #define TOD_CONV_PAIR_ON 8
 #define TOD_CONV_PAIR_OFF 16
 
+/*
+ * SM budget of the persistent kernels' grids (convs, stem): 0 = the whole device (default; TOD_SM_BUDGET overrides the
+ * default).  Read at enqueue / graph-capture time.  K batches in flight on K streams with a budget of #SMs / K each run side
+ * by side on disjoint SMs, every CTA living K times longer: the per-launch cost of a CTA (prologue, wait for the previous
+ * grid, first-load latency, drain of the last accumulator) is amortised over K times more tiles.  The reference has no
+ * counterpart (its layers are cuDNN / ATen launches, model/blocks.py:52-54); results do not depend on it.
+ */
+int tod_set_sm_budget(int32_t sms);
+int tod_get_sm_budget(void);
+
 int tod_conv2d_nhwc_bf16(const tod_conv_desc* desc, void* stream);
 
 /*

@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cstdlib>
+
 #include "tod_common.cuh"
 
 namespace tod {
@@ -36,7 +38,25 @@ TimelineTag timeline_tag(const char* name) {
   return t;
 }
 
+// ---- SM budget of the persistent kernels' grids (tma_host.cuh: num_sms)
+static int g_sm_budget = -1;
+int sm_budget_value() {
+  if (g_sm_budget < 0) {
+    const char* e = getenv("TOD_SM_BUDGET");
+    g_sm_budget = (e != nullptr) ? atoi(e) : 0;
+    if (g_sm_budget < 0) g_sm_budget = 0;
+  }
+  return g_sm_budget;
+}
+
 }  // namespace tod
+
+extern "C" int tod_set_sm_budget(int32_t sms) {
+  TOD_CHECK_ARG(sms >= 0, "tod_set_sm_budget: negative budget");
+  tod::g_sm_budget = sms;
+  return TOD_OK;
+}
+extern "C" int tod_get_sm_budget(void) { return tod::sm_budget_value(); }
 
 extern "C" int tod_debug_set_timeline(void* d_buf) {
   tod::g_timeline = reinterpret_cast<unsigned long long*>(d_buf);

@@ -393,9 +393,7 @@ static int launch_stem_u8(const uint8_t* d_x, const float* h_w, const float* h_b
   const long long total = static_cast<long long>(batch) * (hin / 2) * (win / 2);
   const long long tiles = (total + 127) / 128;
   TOD_CHECK_ARG(total < (1ll << 31), "stem_u8: too many output pixels");
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-    sms = 148;
+  const int sms = num_sms();   // (the SM budget of the launch: tma_host.cuh)
   // CTAs per SM: bounded by TMEM (512 columns) and by what hides the build -> MMA -> epilogue latency chain
   constexpr int kCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : 128);
   const int per_sm = 512 / kCols < 8 ? 512 / kCols : 8;

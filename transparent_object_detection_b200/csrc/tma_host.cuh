@@ -157,6 +157,13 @@ inline bool flat_tiles_enabled() {
   return on == 1;
 }
 
+// SM budget of one launch (tod_set_sm_budget / TOD_SM_BUDGET; 0 = the whole device).  The persistent kernels size their
+// grids by it.  K independent plans (batches in flight on K streams) with a budget of #SMs / K each run side by side on
+// disjoint SMs: every CTA then lives K times longer, so what a CTA pays once per launch -- prologue, the wait for the
+// previous grid, the latency of its first loads, the drain of its last accumulator: ~8-10 us of a ~35 us CTA, during which
+// its SM's tensor pipe idles -- is amortised over K times more tiles.
+int sm_budget_value();   // capi.cu
+
 inline int num_sms() {
   static int sms[64] = {0};
   const int dev = current_device_index();
@@ -165,7 +172,8 @@ inline int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     sms[dev] = n;
   }
-  return sms[dev];
+  const int budget = sm_budget_value();
+  return (budget > 0 && budget < sms[dev]) ? budget : sms[dev];
 }
 
 inline int pick_block_k(int cin, int hint) {
