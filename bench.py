@@ -248,13 +248,9 @@ def run_config3(args, rank, local_rank, world):
     det = Detector(model, (args.size, args.size), confidence=CONF, nms_iou=IOU, letterbox_image=True, pipeline_depth=args.depth)
     B, total = args.batch, args.images
     assert total % B == 0
-    lo, hi = shard_range(total, rank, world)
-    assert lo % B == 0 and hi % B == 0, "image ranges must be whole batches"
 
     def host_batch(j):
         return torch.from_numpy(synth.make_images_u8(B, args.size, args.size, seed=4 + j)).pin_memory()
-
-    mine = [host_batch(j) for j in range(lo // B, hi // B)]
 
     def run(batches):
         out, inflight = [], []
@@ -266,6 +262,29 @@ def run_config3(args, rank, local_rank, world):
             out += det.collect(p)
         return out
 
+    lo, hi = shard_range(total, rank, world)
+    rates = None
+    if args.balance and world > 1:
+        # --balance: contiguous ranges sized by each rank's measured capacity (whole batches).  Calibration = every rank pushes
+        # the same 8 batches through the same pipeline AT THE SAME TIME, so a rank's rate includes what the host fabric gives
+        # its GPU while all the others upload too (on the 8-GPU guest: 20 vs 36 GB/s).
+        calib = [host_batch(10_000 + j) for j in range(2)] * 4
+        run(calib[:det.pipeline_depth + 1])                     # graph capture
+        torch.cuda.synchronize()
+        dist.barrier()
+        tc = time.perf_counter()
+        run(calib)
+        torch.cuda.synchronize()
+        mine_rate = len(calib) * B / (time.perf_counter() - tc)
+        rt = torch.zeros(world, dtype=torch.float64, device=dev)
+        rt[rank] = mine_rate
+        dist.all_reduce(rt)
+        rates = [float(v) for v in rt]
+        from transparent_object_detection_b200 import weighted_shard_ranges
+        lo, hi = weighted_shard_ranges(total, rates, granule=B)[rank]
+        del calib
+    assert lo % B == 0 and hi % B == 0, "image ranges must be whole batches"
+    mine = [host_batch(j) for j in range(lo // B, hi // B)]
     run(mine[:min(len(mine), det.pipeline_depth + 1)])          # graph capture + warm-up
     torch.cuda.synchronize()
     if world > 1:
@@ -297,13 +316,18 @@ def run_config3(args, rank, local_rank, world):
         line = {"metric": "images/sec @640^2 (fwd+decode+NMS), BASELINE config 3", "value": total / wall, "unit": "images/s",
                 "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"config 3: {total} synthetic {args.size}x{args.size} images (batch j = seed 4 + j), scale {args.scale}, "
-                                       f"contiguous ranges of {(hi - lo)} images per rank in batches of {B}, Detector.submit/collect "
+                                       f"contiguous ranges of {'capacity-weighted sizes' if rates else (hi - lo)} images per rank in batches of {B}, Detector.submit/collect "
                                        f"({det.pipeline_depth} in flight) from pinned host uint8, host gather in rank order"},
                 "wall_s": wall, "slowest_rank_s": t_rank_max, "gather_s": gather_s,
                 "timing": "host clock: barrier -> every rank's detections in host memory -> barrier (max over ranks)",
                 "detections": int(sum(0 if r is None else len(r) for r in gathered)),
                 "checksum_sharded": sharded_sum, "checksum_single_gpu": single_sum, "equals_single_gpu_result": bool(equal),
-                "numa_node_rank0": numa_node}
+                "numa_node_rank0": numa_node,
+                "balance": None if rates is None else {"what": "contiguous ranges sized by each rank's calibrated images/s (8 batches through the "
+                                                                "same pipeline on every rank at once), whole batches, largest remainder first",
+                                                        "images_per_s_per_rank": rates,
+                                                        "images_per_rank": [h_ - l_ for l_, h_ in
+                                                                            __import__("transparent_object_detection_b200").weighted_shard_ranges(total, rates, granule=B)]}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -330,6 +354,8 @@ def main():
     ap.add_argument("--breakdown", default="", help="write the per-op eager timing table to this JSON file")
     ap.add_argument("--config3", action="store_true", help="BASELINE config 3 (strong scaling over --images images, host gather)")
     ap.add_argument("--images", type=int, default=4096)
+    ap.add_argument("--balance", action="store_true",
+                    help="config 3: size the contiguous rank ranges by each rank's calibrated capacity instead of equally")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -552,6 +552,33 @@ def test_sharded_image_ranges_equal_the_single_batch_result():
         assert_dets_equal(parts, whole)
 
 
+def test_sm_budget_changes_the_grids_not_the_results():
+    """tod_set_sm_budget(n): the persistent kernels (stem, convs) size their grids by n SMs -- several batches in flight can
+    then share the device side by side.  Which CTA computes a tile never changes what is computed: detections must be
+    bit-identical for every budget (and the budget is read at capture time, so each Detector captures its own graphs)."""
+    import transparent_object_detection_b200 as T
+    from oracle import synth
+    L = T.lib()
+    C_, d, m = synth.SCALES["n"]
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()}
+    x = torch.from_numpy(synth.make_images_u8(6, 160, 224, seed=9))
+    try:
+        results = []
+        for budget in (0, 37, 5, 1):
+            assert L.tod_set_sm_budget(budget) == 0 and L.tod_get_sm_budget() == budget
+            model = T.BaseModel(80, C_, d, m).eval()          # a fresh plan: engines and their graphs are cached per model
+            model.load_state_dict(sd)
+            det = T.Detector(model, (160, 224), confidence=0.01, nms_iou=0.5)
+            results.append(det.detect(x))
+        assert sum(r is not None for r in results[0]) > 0
+        for r in results[1:]:
+            assert_dets_equal(r, results[0])
+        assert L.tod_set_sm_budget(-1) != 0          # rejected, the budget stays
+        assert L.tod_get_sm_budget() == 1
+    finally:
+        L.tod_set_sm_budget(0)
+
+
 def test_network_1280_config4_against_live_oracle():
     """BASELINE config 4 geometry (1280x1280: A = 33600, SPPF planes 40x40) at scale n, one image, against the CPU
     oracle evaluated in the test: boxes <= 1 px, scores <= 5e-3; NMS on OUR decoded tensor bit-exact with the oracle's."""

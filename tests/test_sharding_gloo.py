@@ -57,6 +57,26 @@ def test_shard_ranges_tile_the_batch():
         shard_range(8, 2, 2)
 
 
+def test_weighted_shard_ranges_follow_capacity_in_whole_batches():
+    from transparent_object_detection_b200.sharding import weighted_shard_ranges
+    # the measured 8-GPU guest: four GPUs upload at 20.4 GB/s (16.6 k images/s), four are compute-bound at 22.4 k images/s
+    caps = [16.6e3] * 4 + [22.4e3] * 4
+    spans = weighted_shard_ranges(4096, caps, granule=64)
+    sizes = [h - l for l, h in spans]
+    assert spans[0][0] == 0 and spans[-1][1] == 4096 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert all(sz % 64 == 0 for sz in sizes) and sizes[:4] == [448] * 4 and sizes[4:] == [576] * 4
+    # makespan: equal ranges wait for the slow ranks, weighted ranges finish together
+    assert max(sz / c for sz, c in zip(sizes, caps)) < 0.9 * max(512 / c for c in caps)
+    # equal capacities reduce to the plain partition; a zero-capacity rank gets nothing; remainders go to the largest fraction
+    assert weighted_shard_ranges(4096, [1.0] * 8, 64) == [(r * 512, (r + 1) * 512) for r in range(8)]
+    assert weighted_shard_ranges(10, [1, 0, 1]) == [(0, 5), (5, 5), (5, 10)]
+    assert [h - l for l, h in weighted_shard_ranges(7, [3, 2, 2])] == [3, 2, 2]
+    for bad in (lambda: weighted_shard_ranges(100, [1, 1], 64), lambda: weighted_shard_ranges(64, [], 64),
+                lambda: weighted_shard_ranges(64, [0, 0], 64), lambda: weighted_shard_ranges(64, [1, float("nan")], 64)):
+        with pytest.raises(ValueError):
+            bad()
+
+
 def test_gather_without_process_group_is_identity():
     from transparent_object_detection_b200.sharding import gather_detections
     rows = [None, np.ones((2, 6), np.float32)]

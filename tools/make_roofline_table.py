@@ -46,8 +46,8 @@ if tl:
     print("\n## Inside the captured graph (tools/timeline.py: one record per CTA, two plans alternating)\n")
     print("`pdl` = CTA start -> programmatic-launch wait returned; `fill` = -> first accumulator complete; `steady` = first -> last accumulator; "
           "`drain` = last accumulator -> CTA exit; GHz = SM cycle counter / globaltimer over the CTA.\n")
-    print("| launch | kernel | CTAs/launch | µs per CTA | pdl | fill | steady | drain | GHz |")
-    print("|---:|---|---:|---:|---:|---:|---:|---:|---:|")
+    print("| launch | kernel | CTAs/launch | span µs (first CTA start -> last CTA end) | µs per CTA | pdl | fill | steady | drain | GHz |")
+    print("|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|")
     reps = tl["args"]["replays"] // tl["args"]["plans"]
     seen = set()
     for r in tl["launches"]:
@@ -57,7 +57,7 @@ if tl:
         if key in seen:
             continue
         seen.add(key)
-        print(f"| {r['id']} | {r['name']} | {r['ctas'] // max(reps, 1)} | {r['cta_us_mean']:.1f} | {r['wait_us']:.1f} | {r['fill_us']:.1f} | "
+        print(f"| {r['id']} | {r['name']} | {r['ctas'] // max(reps, 1)} | {r.get('span_us', 0):.1f} | {r['cta_us_mean']:.1f} | {r['wait_us']:.1f} | {r['fill_us']:.1f} | "
               f"{r.get('steady_us', 0):.1f} | {r.get('drain_us', 0):.1f} | {r.get('ghz', 0):.2f} |")
         if r["name"].startswith("nms segments"):
             break

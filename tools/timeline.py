@@ -122,19 +122,25 @@ def main():
         rdy, acc = t_ready[sel], t_acc[sel]
         wait_us = float(np.where(rdy > 0, rdy - t0[sel], 0).mean() / 1e3)          # CTA start -> programmatic-launch wait returned
         fill_us = float(np.where((acc > 0) & (rdy > 0), acc - rdy, 0).mean() / 1e3)  # -> first complete accumulator
+        # in-graph duration of one launch: the records of an id form one cluster per replay of its graph
+        o_ = np.argsort(t0[sel])
+        ts0, ts1 = t0[sel][o_], t1[sel][o_]
+        cuts = np.nonzero(np.diff(ts0) > 400000)[0] + 1          # a new replay starts > 0.4 ms after the previous CTA start
+        spans = [float(ts1[a_:b_].max() - ts0[a_:b_].min()) / 1e3 for a_, b_ in zip(np.r_[0, cuts], np.r_[cuts, len(ts0)]) if b_ > a_]
+        span_us = float(np.median(spans)) if spans else 0.0
         mma_end, last = t_mma[sel], t_last[sel]
         steady_us = float(np.where((last > 0) & (acc > 0), last - acc, 0).mean() / 1e3)      # first -> last accumulator complete
         drain_us = float(np.where(last > 0, t1[sel] - last, 0).mean() / 1e3)                # last accumulator -> CTA end
         mma_tail_us = float(np.where(mma_end > 0, t1[sel] - mma_end, 0).mean() / 1e3)       # MMA role done -> CTA end
-        rows.append({"steady_us": steady_us, "drain_us": drain_us, "mma_tail_us": mma_tail_us,
+        rows.append({"steady_us": steady_us, "drain_us": drain_us, "mma_tail_us": mma_tail_us, "span_us": span_us,
                      "ghz": (ghz_num[int(i)] / ghz_den[int(i)]) if ghz_den.get(int(i)) else 0.0,
                      "id": int(i), "name": names[i] if i < len(names) else "?", "ctas": int(sel.sum()),
                      "cta_us_mean": float(dur.mean() / 1e3), "cta_us_max": float(dur.max() / 1e3), "wait_us": wait_us, "fill_us": fill_us,
                      "sm_time_share": float(dur.sum() / total_cta_ns), "sm_us_per_step": float(dur.sum() / 1e3 / n_sm / a.replays * 1.0)})
     # one graph = one set of ids per plan; fold the plans' copies of the same layer together by name order
-    print(f"{'launch':>6s} {'kernel':40s} {'CTAs':>7s} {'us/CTA':>8s} {'max':>8s} {'pdl-wait':>9s} {'fill':>6s} {'steady':>7s} {'drain':>6s} {'GHz':>5s} {'SM-us/step':>11s} {'share':>7s}")
+    print(f"{'launch':>6s} {'kernel':40s} {'CTAs':>7s} {'span us':>8s} {'us/CTA':>8s} {'max':>8s} {'pdl-wait':>9s} {'fill':>6s} {'steady':>7s} {'drain':>6s} {'GHz':>5s} {'SM-us/step':>11s} {'share':>7s}")
     for r in rows:
-        print(f"{r['id']:6d} {r['name']:40s} {r['ctas']:7d} {r['cta_us_mean']:8.1f} {r['cta_us_max']:8.1f} {r['wait_us']:9.1f} {r['fill_us']:6.1f} "
+        print(f"{r['id']:6d} {r['name']:40s} {r['ctas']:7d} {r['span_us']:8.1f} {r['cta_us_mean']:8.1f} {r['cta_us_max']:8.1f} {r['wait_us']:9.1f} {r['fill_us']:6.1f} "
               f"{r['steady_us']:7.1f} {r['drain_us']:6.1f} {r['ghz']:5.2f} {r['sm_us_per_step']:11.1f} {100 * r['sm_time_share']:6.2f}%")
     by_name = {}
     for r in rows:

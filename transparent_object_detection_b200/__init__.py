@@ -9,7 +9,7 @@ alternative-backend fallback.
 from .model import BaseModel, DecodeBox, Detector, parameter_table  # noqa: F401
 from .engine import DetectorEngine, fold_conv_bn, pack_conv_weight  # noqa: F401
 from ._lib import lib, LIB_PATH, SYMBOLS, TodError  # noqa: F401
-from .sharding import shard_range, gather_detections  # noqa: F401
+from .sharding import shard_range, weighted_shard_ranges, gather_detections  # noqa: F401
 
 __all__ = ["BaseModel", "DecodeBox", "Detector", "DetectorEngine", "lib", "LIB_PATH", "SYMBOLS", "TodError",
-           "shard_range", "gather_detections"]
+           "shard_range", "weighted_shard_ranges", "gather_detections"]
