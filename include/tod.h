@@ -229,6 +229,16 @@ int tod_decode_box_from_head(const float* d_head_out, float* d_decoded, int32_t 
                              int32_t in_h, int32_t in_w, void* stream);
 
 /*
+ * Loss.bbox_decode (model/loss.py:333-337; SURVEY 8 row f4, forward only): pred_dist f32 [batch, anchors, 4 * reg_max] logits
+ * (the box half of the training-mode head maps, model/head.py:50-51, flattened and permuted as loss.py:343-347 does) ->
+ * softmax over the reg_max bins of each side . arange(reg_max) -> dist2bbox(xywh=False) about anchor_points f32 [anchors, 2]
+ * (make_anchors, utils/bbox_utils.py:14-37): out f32 [batch, anchors, 4] = (x1, y1, x2, y2) in grid units.
+ * reg_max == 1: the distances are taken as they are (use_dfl False).
+ */
+int tod_loss_bbox_decode(const float* d_pred_dist, const float* d_anchor_points, float* d_out, int32_t batch, int32_t anchors,
+                         int32_t reg_max, void* stream);
+
+/*
  * DecodeBox.decode_box on the upstream 5-tuple the reference's callers are written for (utils/bbox_utils.py:66-82;
  * callers utils/callbacks.py:150-151, dataset/coco/get_map.py:68-69): (dbox, cls, origin_cls, anchors, strides) ->
  * d_decoded f32 [batch, A, 4+nc] = cat(dist2bbox(dbox, anchors, xywh) * strides, sigmoid(cls)).permute(0, 2, 1) with

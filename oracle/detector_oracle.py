@@ -253,6 +253,17 @@ def decode_box_tuple(dbox: torch.Tensor, cls: torch.Tensor, anchors: torch.Tenso
     return y
 
 
+def loss_bbox_decode(anchor_points: torch.Tensor, pred_dist: torch.Tensor, reg_max: int = 16) -> torch.Tensor:
+    """reference Loss.bbox_decode, model/loss.py:333-337: pred_dist (B, A, 4 * reg_max) logits -> softmax over the bins of each
+    side, `.matmul(proj)` with proj = arange(reg_max), then dist2bbox(xywh=False) (utils/bbox_utils.py:51-55 with the default
+    dim -1) about anchor_points (A, 2) -> (B, A, 4) corners in grid units.  reg_max == 1 (use_dfl False): no softmax."""
+    if reg_max > 1:
+        b, a, c = pred_dist.shape
+        pred_dist = pred_dist.view(b, a, 4, c // 4).softmax(3).matmul(torch.arange(reg_max, dtype=pred_dist.dtype))
+    lt, rb = torch.split(pred_dist, 2, -1)
+    return torch.cat((anchor_points - lt, anchor_points + rb), -1)
+
+
 # ----------------------------------------------------------------------------- NMS
 def nms_greedy(boxes: np.ndarray, scores: np.ndarray, iou_thr: float) -> np.ndarray:
     """torchvision.ops.nms CPU semantics (called at utils/bbox_utils.py:172), restated.

@@ -552,6 +552,26 @@ def test_sharded_image_ranges_equal_the_single_batch_result():
         assert_dets_equal(parts, whole)
 
 
+@pytest.mark.parametrize("case,reg_max", [("net", 16), ("syn", 16), ("nodfl", 1)])
+@pytest.mark.parametrize("on_cpu", [False, True], ids=["cuda_in", "cpu_in"])
+def test_loss_bbox_decode_vs_reference_fixture(golden, case, reg_max, on_cpu):
+    """LossDecode.bbox_decode (tod_loss_bbox_decode) against the reference's own Loss.bbox_decode
+    (model/loss.py:333-337; fixture from oracle/make_golden_loss.py).  float32, stated tolerance 2e-5 grid units absolute
+    (the reference's `.softmax(3).matmul(proj)` sums its 16 terms in ATen's order; the kernel sums them in index order)."""
+    import transparent_object_detection_b200 as T
+    g = golden("loss_bbox_decode.npz")
+    ap, pd, want = (torch.from_numpy(g[f"{case}_{k}"]) for k in ("anchor_points", "pred_dist", "boxes"))
+    head = type("H", (), {"ch": reg_max, "nc": 80, "stride": [8, 16, 32]})()
+    ld = T.LossDecode(type("M", (), {"head": head})())
+    assert ld.reg_max == reg_max and ld.use_dfl == (reg_max > 1)
+    got = ld.bbox_decode(ap if on_cpu else ap.cuda(), pd if on_cpu else pd.cuda())
+    assert got.is_cuda != on_cpu and tuple(got.shape) == tuple(want.shape)
+    err = float((got.cpu() - want).abs().max())
+    assert err <= (2e-5 if reg_max > 1 else 0.0), err
+    with pytest.raises(ValueError):
+        ld.bbox_decode(ap, pd[:, :, :-1])
+
+
 def test_sm_budget_changes_the_grids_not_the_results():
     """tod_set_sm_budget(n): the persistent kernels (stem, convs) size their grids by n SMs -- several batches in flight can
     then share the device side by side.  Which CTA computes a tile never changes what is computed: detections must be

@@ -189,3 +189,12 @@ def test_decode_box_tuple_oracle_bit_exact_vs_reference(golden, case):
     want = g[f"{case}_decoded"]
     assert np.array_equal(got.numpy()[:, :, :4], want[:, :, :4])          # add / sub / mul / div only: bit-exact anywhere
     assert np.abs(got.numpy()[:, :, 4:] - want[:, :, 4:]).max() <= 1e-6   # sigmoid: the host's vector exp may differ by ulps
+
+
+def test_oracle_loss_bbox_decode_matches_reference_fixture(golden):
+    """the oracle's restatement of Loss.bbox_decode (model/loss.py:333-337) against the fixture written from
+    the reference's own method (oracle/make_golden_loss.py) -- same torch ops, so bit for bit."""
+    g = golden("loss_bbox_decode.npz")
+    for case, reg_max in (("net", 16), ("syn", 16), ("nodfl", 1)):
+        got = O.loss_bbox_decode(torch.from_numpy(g[case + "_anchor_points"]), torch.from_numpy(g[case + "_pred_dist"]), reg_max)
+        assert np.array_equal(got.numpy(), g[case + "_boxes"]), case

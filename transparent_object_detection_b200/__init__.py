@@ -6,10 +6,10 @@ mohamed22311/Transparent-Object-Detection: forward -> decode -> NMS behind the r
 All arithmetic runs in libtod.so (hand-written CUDA, C ABI in include/tod.h); there is no CPU or
 alternative-backend fallback.
 """
-from .model import BaseModel, DecodeBox, Detector, parameter_table  # noqa: F401
+from .model import BaseModel, DecodeBox, Detector, LossDecode, parameter_table  # noqa: F401
 from .engine import DetectorEngine, fold_conv_bn, pack_conv_weight  # noqa: F401
 from ._lib import lib, LIB_PATH, SYMBOLS, TodError  # noqa: F401
 from .sharding import shard_range, weighted_shard_ranges, gather_detections  # noqa: F401
 
-__all__ = ["BaseModel", "DecodeBox", "Detector", "DetectorEngine", "lib", "LIB_PATH", "SYMBOLS", "TodError",
+__all__ = ["BaseModel", "DecodeBox", "Detector", "LossDecode", "DetectorEngine", "lib", "LIB_PATH", "SYMBOLS", "TodError",
            "shard_range", "weighted_shard_ranges", "gather_detections"]

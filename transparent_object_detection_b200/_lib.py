@@ -20,7 +20,7 @@ SYMBOLS = (
     "tod_conv2d_tail1x1_box_decode", "tod_cbam_workspace_floats", "tod_cbam_nhwc_bf16",
     "tod_softmax_rows_f32_bf16", "tod_attention_fused", "tod_transpose_bf16", "tod_decode_box_from_tuple",
     "tod_pack_workspace_bytes", "tod_pack_detections", "tod_debug_set_timeline", "tod_debug_timeline_launches",
-    "tod_debug_timeline_name", "tod_set_sm_budget", "tod_get_sm_budget",
+    "tod_debug_timeline_name", "tod_set_sm_budget", "tod_get_sm_budget", "tod_loss_bbox_decode",
 )
 
 
@@ -138,6 +138,7 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_int64, C.c_void_p]
     L.tod_debug_set_conv_profile.argtypes = [C.c_void_p]
     L.tod_set_sm_budget.argtypes = [C.c_int32]
+    L.tod_loss_bbox_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.tod_debug_set_timeline.argtypes = [C.c_void_p]
     L.tod_debug_timeline_name.argtypes = [C.c_int]
     L.tod_debug_timeline_name.restype = C.c_char_p

@@ -241,9 +241,56 @@ __global__ void __launch_bounds__(256) decode_tuple_kernel(const float* __restri
   for (int i = threadIdx.x; i < n_valid; i += 256) dst[i] = rows[i];
 }
 
+// Loss.bbox_decode (model/loss.py:333-337): pred_dist (B, A, 4 * reg_max) logits -> softmax over the reg_max bins of each
+// side, projection on arange(reg_max) (`.softmax(3).matmul(proj)`), then dist2bbox(xywh=False) about anchor_points (A, 2):
+// (B, A, 4) corner boxes in grid units.  One thread per (image, anchor, side): side 0 / 1 -> anchor - (l, t), side 2 / 3 ->
+// anchor + (r, b); a warp reads 8 contiguous anchor rows.  reg_max == 1 (use_dfl False) passes the distances through.
+__global__ void __launch_bounds__(256) loss_bbox_decode_kernel(const float* __restrict__ pred_dist, const float* __restrict__ anchor_points,
+                                                               float* __restrict__ out, long long total_sides, int anchors, int reg_max) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;      // (b * A + a) * 4 + side
+  const bool on = i < total_sides;
+  const long long row = (on ? i : 0) >> 2;
+  const int side = static_cast<int>(i & 3);
+  float dist;
+  if (reg_max == 1) {
+    dist = on ? pred_dist[i] : 0.f;
+  } else {
+    const float* l = pred_dist + (on ? i : 0) * reg_max;
+    float m = -INFINITY;
+    for (int k = 0; k < reg_max; ++k) m = fmaxf(m, l[k]);
+    float sum = 0.f, wsum = 0.f;
+    for (int k = 0; k < reg_max; ++k) {            // softmax terms e / sum, then the dot with arange: sum_k k * (e_k / sum)
+      const float e = expf(__fsub_rn(l[k], m));
+      sum = __fadd_rn(sum, e);
+    }
+    for (int k = 0; k < reg_max; ++k) {
+      const float pk = __fdiv_rn(expf(__fsub_rn(l[k], m)), sum);
+      wsum = __fadd_rn(wsum, __fmul_rn(pk, static_cast<float>(k)));
+    }
+    dist = wsum;
+  }
+  // side 0/1 -> anchor - lt, side 2/3 -> anchor + rb   (dist2bbox, xywh=False, utils/bbox_utils.py:51-55)
+  const int a = static_cast<int>(row % anchors);
+  const float ap = anchor_points[2 * a + (side & 1)];
+  const float v = side < 2 ? __fsub_rn(ap, dist) : __fadd_rn(ap, dist);
+  if (on) out[i] = v;
+}
+
 }  // namespace tod
 
 using namespace tod;
+
+extern "C" int tod_loss_bbox_decode(const float* d_pred_dist, const float* d_anchor_points, float* d_out, int32_t batch,
+                                    int32_t anchors, int32_t reg_max, void* stream) {
+  TOD_CHECK_ARG(d_pred_dist && d_anchor_points && d_out, "loss bbox_decode: null pointer");
+  TOD_CHECK_ARG(batch > 0 && anchors > 0 && reg_max >= 1 && reg_max <= 64, "loss bbox_decode: bad shape");
+  const long long total = static_cast<long long>(batch) * anchors * 4;
+  TOD_CHECK_ARG(total < (1ll << 38), "loss bbox_decode: too many boxes");
+  loss_bbox_decode_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_pred_dist, d_anchor_points, d_out, total, anchors, reg_max);
+  TOD_CHECK_LAUNCH("loss_bbox_decode_kernel launch");
+  return TOD_OK;
+}
 
 extern "C" int tod_decode_box_from_tuple(const float* d_dbox, const float* d_cls, const float* d_anchors, const float* d_strides,
                                          float* d_decoded, int32_t batch, int32_t nc, int32_t anchors, int32_t in_h,

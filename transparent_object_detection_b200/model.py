@@ -179,6 +179,39 @@ class BaseModel(nn.Module):
         return self
 
 
+# ----------------------------------------------------------------------------------- loss-side decode
+class LossDecode:
+    """Forward-only counterpart of the decode inside the reference's `Loss` (model/loss.py:303-337): same constructor
+    argument (a model whose head carries `stride`, `nc`, `ch`) and the same `bbox_decode(anchor_points, pred_dist)`
+    signature / return value; the arithmetic runs in libtod.so (tod_loss_bbox_decode).  No autograd: training is out of
+    scope, this is the consumer the training-mode head maps (model/head.py:50-51) were defined for."""
+
+    def __init__(self, model=None, reg_max: int = 16):
+        head = getattr(model, "head", None)
+        self.reg_max = int(getattr(head, "ch", reg_max)) if head is not None else int(reg_max)
+        self.use_dfl = self.reg_max > 1
+        self.proj = torch.arange(self.reg_max, dtype=torch.float)
+
+    def bbox_decode(self, anchor_points: torch.Tensor, pred_dist: torch.Tensor) -> torch.Tensor:
+        """model/loss.py:333-337: pred_dist (B, A, 4 * reg_max) -> (B, A, 4) corner boxes in grid units about anchor_points (A, 2)."""
+        if pred_dist.dim() != 3 or pred_dist.shape[2] != 4 * self.reg_max:
+            raise ValueError(f"bbox_decode expects pred_dist (B, A, {4 * self.reg_max}), got {tuple(pred_dist.shape)}")
+        B, A, _ = pred_dist.shape
+        if anchor_points.numel() != 2 * A:
+            raise ValueError(f"bbox_decode: anchor_points {tuple(anchor_points.shape)} do not match A = {A}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("LossDecode.bbox_decode needs a CUDA device: there is no CPU path")
+        was_cpu = not pred_dist.is_cuda
+        dev = pred_dist.device if pred_dist.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        pd = pred_dist.detach().to(dev, torch.float32).contiguous()
+        ap = anchor_points.detach().to(dev, torch.float32).reshape(A, 2).contiguous()
+        out = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().tod_loss_bbox_decode(pd.data_ptr(), ap.data_ptr(), out.data_ptr(), B, A, self.reg_max,
+                                                  torch.cuda.current_stream().cuda_stream), "tod_loss_bbox_decode")
+        return out.cpu() if was_cpu else out
+
+
 # ----------------------------------------------------------------------------------- DecodeBox
 class DecodeBox:
     """B200 drop-in for reference `DecodeBox` (utils/bbox_utils.py:61-182)."""
