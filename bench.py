@@ -520,6 +520,39 @@ def main():
             print(json.dumps({"error": "captured-graph detections differ from the eager API chain", "parity": parity}), flush=True)
             raise SystemExit(3)
 
+    # ---------------------------------------------------------------- the reference's own call chain, unchanged (rank 0)
+    api_chain = None
+    if rank == 0 and not args.attention:
+        # what a maintainer gets from the import swap alone (utils/callbacks.py:147-154):
+        # net(images) -> bbox_util.decode_box -> bbox_util.non_max_suppression on a device-resident float32 (B,3,H,W)
+        # tensor; eager launches, the (B, 4+nc, A) head tensor and the decoded tensor are materialised, rows come back as
+        # the reference's list of numpy arrays
+        try:
+            db2 = DecodeBox(80, (args.size, args.size))
+            xf = torch.from_numpy(synth.images_u8_to_f32(hosts[0].numpy())).to(dev)
+            ishape = np.array((args.size, args.size))
+
+            def chain_once():
+                with torch.no_grad():
+                    out = model(xf)
+                    return db2.non_max_suppression(db2.decode_box(out), 80, (args.size, args.size), ishape, True,
+                                                   conf_thres=CONF, nms_thres=IOU)
+            chain_once()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                rows_c = chain_once()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            api_chain = {"what": "net(x) -> DecodeBox.decode_box -> DecodeBox.non_max_suppression, the reference's call chain on a "
+                                 "device-resident float32 batch (eager launches, head + decoded tensors materialised, rows to host)",
+                         "ms_per_batch": 1e3 * float(np.median(ts)), "value": B / float(np.median(ts)), "unit": "images/s",
+                         "kept_per_image": float(np.mean([0 if r is None else len(r) for r in rows_c]))}
+            del xf
+        except Exception as e:
+            api_chain = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---------------------------------------------------------------- per-op eager pass (kernel-level roofline)
     table = []
     if rank == 0:
@@ -663,7 +696,8 @@ def main():
                                       "h2d_gb_per_s": hosts_f32[0].numel() * 4 / (e2e_f32_ms / 1e3) / 1e9,
                                       "api": "Detector.submit/collect (same pipeline) on the reference's float32 (B,3,H,W) tensor: PCIe-bound"}},
                 "gpu_launches": eng.launches_per_pass * K,
-                "clocks": sampler.result(), "roofline": roof, "parity": parity, "library_baseline": lib, "cpu_baseline": cpu,
+                "clocks": sampler.result(), "roofline": roof, "parity": parity, "api_chain": api_chain,
+                "library_baseline": lib, "cpu_baseline": cpu,
                 "breakdown_ms": {"conv": conv_ms, "stem": sum(r["ms"] for r in table if r["kind"] == "stem"),
                                  "pool": sum(r["ms"] for r in table if r["kind"] == "pool"),
                                  "cbam": sum(r["ms"] for r in table if r["kind"] == "cbam"),
