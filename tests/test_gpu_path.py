@@ -552,6 +552,35 @@ def test_sharded_image_ranges_equal_the_single_batch_result():
         assert_dets_equal(parts, whole)
 
 
+def test_upstream_style_detect_image_and_get_fps(tmp_path):
+    """The facade predict.py is written against (predict.py:105,130,156,168): detect_image(image, crop, count) returns
+    the annotated PIL image -- same size, pixels changed exactly where boxes were kept, crops written -- and get_FPS(image, n)
+    a positive time per image; the get_map form of detect_image keeps working through the same method."""
+    import transparent_object_detection_b200 as T
+    from PIL import Image
+    from oracle import synth
+    C_, d, m = synth.SCALES["n"]
+    model = T.BaseModel(80, C_, d, m).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()})
+    det = T.Detector(model, (160, 224), confidence=0.01, nms_iou=0.5, max_boxes=20)
+    rng = np.random.default_rng(3)
+    img = Image.fromarray(rng.integers(0, 256, (120, 200, 3), dtype=np.uint8))
+    rows = det.top_boxes(det.detect_image_rows(img))
+    assert rows is not None and 0 < len(rows) <= 20
+    out = det.annotate_image(img.copy(), crop=True, count=True, crop_dir=str(tmp_path / "crops"))
+    assert isinstance(out, Image.Image) and out.size == img.size
+    assert np.any(np.asarray(out) != np.asarray(img))
+    assert len(list((tmp_path / "crops").iterdir())) > 0
+    out2 = det.detect_image(img.copy())                      # upstream call form, positional image only
+    assert isinstance(out2, Image.Image) and np.array_equal(np.asarray(out2), np.asarray(det.annotate_image(img.copy())))
+    res = det.detect_image(7, img, [], {i: i + 1 for i in range(80)})          # get_map.py form
+    assert isinstance(res, list) and len(res) > 0 and res[0]["image_id"] == 7 and set(res[0]) == {"image_id", "category_id", "bbox", "score"}
+    t = det.get_FPS(img, 3)
+    assert 0.0 < t < 5.0
+    blank = det.__class__(model, (160, 224), confidence=0.999, nms_iou=0.5)   # nothing passes: the image comes back untouched
+    assert np.array_equal(np.asarray(blank.detect_image(img.copy())), np.asarray(img))
+
+
 @pytest.mark.parametrize("case,reg_max", [("net", 16), ("syn", 16), ("nodfl", 1)])
 @pytest.mark.parametrize("on_cpu", [False, True], ids=["cuda_in", "cpu_in"])
 def test_loss_bbox_decode_vs_reference_fixture(golden, case, reg_max, on_cpu):

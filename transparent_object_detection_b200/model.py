@@ -18,6 +18,9 @@ import ctypes as C
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+import time
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -571,10 +574,86 @@ class Detector:
         """A batch of raw RGB images of any sizes -> the reference's rows per image (device letterbox + network + NMS)."""
         return self.collect(self.submit_images(images))
 
-    def detect_image(self, image_id, image, results: list, clsid2catid) -> list:
-        """reference mAP_FOCUS.detect_image (dataset/coco/get_map.py:37-96): `image` is a PIL image or an
-        (H, W, 3) uint8 array; appends COCO-style dicts to `results`."""
+    # -- the upstream-style facade predict.py is written against (predict.py:105, 130, 156, 168; SURVEY 8b) ---------------
+    def annotate_image(self, image, crop: bool = False, count: bool = False, class_names: Optional[Sequence[str]] = None,
+                       crop_dir: str = "img_crop"):
+        """`model.detect_image(image, crop=crop, count=count)` of predict.py:105,130,168 -> the PIL image with the kept boxes
+        drawn on it (at most `max_boxes`, score descending: utils/callbacks.py:159-166).  The detections come from the same
+        device pipeline as detect_image_rows (device letterbox + network + decode + NMS + un-letterbox); only the drawing is
+        host code (PIL), as upstream.  crop: every box is also saved as `crop_dir`/crop_<i>.png; count: the per-class counts
+        are printed (upstream prints them too)."""
+        from PIL import Image, ImageDraw, ImageFont
+        if not isinstance(image, Image.Image):
+            image = Image.fromarray(np.asarray(image))
+        image = image if image.mode == "RGB" else image.convert("RGB")
+        rows = self.top_boxes(self.detect_image_rows(image))
+        if rows is None:
+            return image
+        names = list(class_names) if class_names is not None else [str(i) for i in range(self.model.num_classes)]
+        top_label, top_conf, top_boxes = np.array(rows[:, 5], dtype="int32"), rows[:, 4], rows[:, :4]
+        w, h = image.size
+        thickness = int(max((w + h) // int(np.mean(self.input_shape)), 1))
+        font = ImageFont.load_default()
+        if count:
+            print("top_label:", top_label)
+            for c in range(self.model.num_classes):
+                n = int(np.sum(top_label == c))
+                if n > 0:
+                    print(names[c], ":", n)
+        boxes = []
+        for i in range(len(top_label)):
+            top, left, bottom, right = top_boxes[i]
+            boxes.append((max(0, int(np.floor(top))), max(0, int(np.floor(left))),
+                          min(h, int(np.floor(bottom))), min(w, int(np.floor(right)))))
+        if crop:
+            os.makedirs(crop_dir, exist_ok=True)
+            for i, (top, left, bottom, right) in enumerate(boxes):
+                if bottom > top and right > left:
+                    image.crop([left, top, right, bottom]).save(os.path.join(crop_dir, f"crop_{i}.png"), quality=95, subsampling=0)
+        draw = ImageDraw.Draw(image)
+        for i, (top, left, bottom, right) in enumerate(boxes):
+            c = int(top_label[i])
+            colour = tuple(int(v) for v in (np.array([37, 91, 173]) * (c + 1)) % 256)
+            label = f"{names[c] if c < len(names) else c} {top_conf[i]:.2f}"
+            for t in range(thickness):
+                draw.rectangle([left + t, top + t, right - t, bottom - t], outline=colour)
+            x0, y0, x1, y1 = draw.textbbox((0, 0), label, font=font)
+            ty = top - (y1 - y0) - 2 if top - (y1 - y0) - 2 >= 0 else top + 1
+            draw.rectangle([left, ty, left + (x1 - x0) + 2, ty + (y1 - y0) + 2], fill=colour)
+            draw.text((left + 1, ty + 1), label, fill=(0, 0, 0), font=font)
+        del draw
+        return image
+
+    def get_FPS(self, image, test_interval: int) -> float:
+        """`model.get_FPS(img, test_interval)` of predict.py:154-157 -> seconds per image at batch size 1: the image is
+        letterboxed once, then network + decode + NMS run `test_interval` times (upstream times exactly that loop), each
+        call returning the rows to the host."""
         from PIL import Image
+        if not isinstance(image, Image.Image):
+            image = Image.fromarray(np.asarray(image))
+        image_shape = np.array(np.shape(image)[0:2])
+        image = image if image.mode == "RGB" else image.convert("RGB")
+        image_data = _letterbox(image, (self.input_shape[1], self.input_shape[0]), self.letterbox_image)
+        x = torch.from_numpy(np.array(image_data, dtype=np.uint8)[None]).pin_memory()
+        self.detect(x, image_shape)                      # graph capture happens outside the timed loop (upstream warms up too)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        for _ in range(int(test_interval)):
+            self.detect(x, image_shape)
+        return (time.time() - t1) / max(int(test_interval), 1)
+
+    def detect_image(self, image_id, image=None, results: Optional[list] = None, clsid2catid=None, *, crop: bool = False,
+                     count: bool = False):
+        """Both call forms the reference's code base uses:
+          * `detect_image(image_id, image, results, clsid2catid)` -- mAP_FOCUS.detect_image (dataset/coco/get_map.py:37-96):
+            `image` is a PIL image or an (H, W, 3) uint8 array; appends COCO-style dicts to `results`;
+          * `detect_image(image, crop=False, count=False)` -- the upstream-style call of predict.py:105,130,168: returns the
+            annotated PIL image (annotate_image)."""
+        from PIL import Image
+        if results is None and clsid2catid is None and (isinstance(image_id, Image.Image) or isinstance(image_id, np.ndarray)):
+            if isinstance(image, bool):                  # detect_image(image, crop) positionally
+                crop = image
+            return self.annotate_image(image_id, crop=crop, count=count)
         if not isinstance(image, Image.Image):
             image = Image.fromarray(np.asarray(image))
         image_shape = np.array(np.shape(image)[0:2])
