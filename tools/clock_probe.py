@@ -20,7 +20,7 @@ from transparent_object_detection_b200._lib import check               # noqa: E
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ops", default="head.cls.0.2,backbone.dark2.1.cv2,backbone.dark4.1.m.0.cv1,backbone.dark3.1.m.0.cv1")
-    ap.add_argument("--seconds", type=float, default=0.6)
+    ap.add_argument("--seconds", type=float, default=1.5)
     a = ap.parse_args()
     C_, d, m = synth.SCALES["s"]
     model = BaseModel(80, C_, d, m).eval()
@@ -44,15 +44,22 @@ def main():
         n = max(50, int(a.seconds * 1e3 / max(e0.elapsed_time(e1), 1e-3)))
         buf.zero_(); buf[1] = cap
         check(L.tod_debug_set_timeline(buf.data_ptr()), "timeline")
-        t0 = time.perf_counter()
-        pw = []
+        pw, stop = [], [False]
+
+        def sample():                      # board power while the GPU works (the host enqueues far ahead of the device)
+            while not stop[0]:
+                pw.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                time.sleep(0.05)
+        import threading
+        th = threading.Thread(target=sample, daemon=True)
         e0.record()
         for i in range(n):
             check(L.tod_conv2d_nhwc_bf16(C.byref(dd), st), name)
-            if i % 200 == 100:
-                pw.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
         e1.record()
+        th.start()
         torch.cuda.synchronize()
+        stop[0] = True
+        th.join()
         check(L.tod_debug_set_timeline(None), "timeline off")
         cnt = min(int(buf[0]), cap)
         rec = buf[2:2 + 8 * cnt].view(-1, 8).cpu().numpy()
@@ -72,8 +79,8 @@ def main():
         ho, wo = dd.hin // dd.stride, dd.win // dd.stride
         gflop = 2.0 * 64 * ho * wo * dd.cout * dd.cin * dd.ksize ** 2 / 1e9
         print(f"{name:28s} {dd.cin}->{dd.cout} k{dd.ksize} @{ho}x{wo}: {n} launches, {ms * 1e3:.1f} us each = {gflop / ms:.0f} TFLOP/s; SM clock "
-              f"first quarter {np.median(ghz_first):.3f} GHz, last quarter {np.median(ghz_last):.3f} GHz; board power samples "
-              f"{np.round(pw, 0).tolist()[:8]} W", flush=True)
+              f"first quarter {np.median(ghz_first):.3f} GHz, last quarter {np.median(ghz_last):.3f} GHz; board power "
+              f"median {np.median(pw) if pw else float('nan'):.0f} W, max {np.max(pw) if pw else float('nan'):.0f} W ({len(pw)} samples)", flush=True)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--no-station", action="store_true")
     ap.add_argument("--trace", type=int, default=0, help="print the first N entries of CTA 0's MMA-group timeline")
+    ap.add_argument("--pair", type=int, default=0, help="1: CTA-pair kernel (TOD_CONV_PAIR_ON), -1: forced off")
     a = ap.parse_args()
     C_, d, m = synth.SCALES[a.scale]
     model = BaseModel(80, C_, d, m).eval()
@@ -47,7 +48,7 @@ def main():
     for kind, name, payload in eng.ops:
         if kind != "conv" or (filt and not any(f in name for f in filt)):
             continue
-        dv = clone_desc(payload, variant=2, m=a.m, no_station=1 if a.no_station else 0)
+        dv = clone_desc(payload, variant=2, m=a.m, no_station=1 if a.no_station else 0, pair=a.pair)
         check(L.tod_conv2d_nhwc_bf16(C.byref(dv), st), name)      # warm
         torch.cuda.synchronize()
         prof.zero_()

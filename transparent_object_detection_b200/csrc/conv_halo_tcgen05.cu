@@ -1585,6 +1585,7 @@ int conv_halo_launch(const tod_conv_desc* d, void* stream, const tod_head_fuse_d
   bool pair = false;
   if (fuse == nullptr && !(d->flags & TOD_CONV_PAIR_OFF) && pair_mode() != 0 && num_sms() >= 2) {
     if ((d->flags & TOD_CONV_PAIR_ON) || pair_mode() == 2) pair = true;
+    else if (pair_mode() == 3) pair = pair_rule(d) || (d->ksize == 3 && d->stride == 1 && d->cin >= 128 && d->cout >= 128);   // A/B
     else pair = pair_rule(d);
   }
   HaloParams p;
