@@ -552,6 +552,30 @@ def test_sharded_image_ranges_equal_the_single_batch_result():
         assert_dets_equal(parts, whole)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process_gives_the_same_detections():
+    """One process driving two GPUs (BaseModel.engine(device=...), Detector on tensors of either device): the one-time kernel
+    attribute setup (dynamic shared memory limits of the tcgen05 / pooling / NMS kernels, CTA-pair instantiations included) is
+    per device, so the second device must run the same plan and return the same rows bit for bit."""
+    import transparent_object_detection_b200 as T
+    from oracle import synth
+    C_, d, m = synth.SCALES["n"]
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(80, C_, d, m, seed=0).items()}
+    x = torch.from_numpy(synth.make_images_u8(4, 160, 160, seed=12))
+    rows = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            model = T.BaseModel(80, C_, d, m).eval()
+            model.load_state_dict(sd)
+            det = T.Detector(model, (160, 160), confidence=0.01, nms_iou=0.5)
+            rows.append(det.detect(x.to(f"cuda:{dev}")))
+            head = model(torch.from_numpy(synth.images_u8_to_f32(x.numpy())).to(f"cuda:{dev}"))
+            rows.append([head.cpu().numpy()])
+    assert sum(r is not None for r in rows[0]) > 0
+    assert_dets_equal(rows[2], rows[0])
+    assert np.array_equal(rows[3][0], rows[1][0])
+
+
 def test_upstream_style_detect_image_and_get_fps(tmp_path):
     """The facade predict.py is written against (predict.py:105,130,156,168): detect_image(image, crop, count) returns
     the annotated PIL image -- same size, pixels changed exactly where boxes were kept, crops written -- and get_FPS(image, n)
