@@ -187,27 +187,25 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_tma_kernel(const __gri
   };
   // one pass along a line of `len` elements `stride` bytes apart: out[i] = max(in[i-2 .. i+2]) clipped to the line (a
   // clipped window == the reference's implicit -inf padding, model/blocks.py:135; a repeated edge element is harmless
-  // under max).  Ten outputs per step from fourteen loads issued together: the loads of a step are independent, so the
-  // shared-memory latency is paid once per step instead of once per element.
-  auto line_pass = [&](uint32_t src, uint32_t dst, int len, uint32_t stride) {
-    constexpr int CH = 10;
-#pragma unroll 1
-    for (int base_i = 0; base_i < len; base_i += CH) {
-      uint4 x[CH + 4];
+  // under max).  A task is ten consecutive outputs of one line, from fourteen loads issued together: the loads are
+  // independent, so the shared-memory latency is paid once per task instead of once per element, and a 20-element line is
+  // two tasks (every thread of the CTA has work in every pass).
+  constexpr int CH = 10;
+  auto chunk_pass = [&](uint32_t src, uint32_t dst, int len, uint32_t stride, int base_i) {
+    uint4 x[CH + 4];
 #pragma unroll
-      for (int j = 0; j < CH + 4; ++j) {
-        const int idx = min(max(base_i + j - 2, 0), len - 1);
-        x[j] = lds(src + static_cast<uint32_t>(idx) * stride);
-      }
-      uint4 m2[CH + 3];
+    for (int j = 0; j < CH + 4; ++j) {
+      const int idx = min(max(base_i + j - 2, 0), len - 1);
+      x[j] = lds(src + static_cast<uint32_t>(idx) * stride);
+    }
+    uint4 m2[CH + 3];
 #pragma unroll
-      for (int j = 0; j < CH + 3; ++j) m2[j] = max_bf16x8(x[j], x[j + 1]);
+    for (int j = 0; j < CH + 3; ++j) m2[j] = max_bf16x8(x[j], x[j + 1]);
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        if (base_i + j < len) {
-          const uint4 m = max_bf16x8(max_bf16x8(m2[j], m2[j + 2]), x[j + 4]);
-          sts(dst + static_cast<uint32_t>(base_i + j) * stride, m);
-        }
+    for (int j = 0; j < CH; ++j) {
+      if (base_i + j < len) {
+        const uint4 m = max_bf16x8(max_bf16x8(m2[j], m2[j + 2]), x[j + 4]);
+        sts(dst + static_cast<uint32_t>(base_i + j) * stride, m);
       }
     }
   };
@@ -215,17 +213,20 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_tma_kernel(const __gri
 #pragma unroll 1
   for (int stage = 1; stage <= 3; ++stage) {
     // row pass b0 -> b1: task = (row y, vector v)
-    for (int tsk = threadIdx.x; tsk < h * VEC; tsk += kPoolThreads) {
-      const int y = tsk / VEC, v = tsk - y * VEC;
+    const int row_chunks = (w + CH - 1) / CH, col_chunks = (h + CH - 1) / CH;
+    for (int tsk = threadIdx.x; tsk < h * VEC * row_chunks; tsk += kPoolThreads) {
+      const int line = tsk % (h * VEC), chunk = tsk / (h * VEC);
+      const int y = line / VEC, v = line - y * VEC;
       const uint32_t off = static_cast<uint32_t>(y) * row_bytes + v * 16u;
-      line_pass(b0 + off, b1 + off, w, px_bytes);
+      chunk_pass(b0 + off, b1 + off, w, px_bytes, chunk * CH);
     }
     if (threadIdx.x == 0) bulk_wait_read_all();   // the previous stage's store has finished reading b0
     __syncthreads();
     // column pass b1 -> b0: task = (column x, vector v)
-    for (int tsk = threadIdx.x; tsk < w * VEC; tsk += kPoolThreads) {
-      const uint32_t off = static_cast<uint32_t>(tsk) * 16u;   // (x * VEC + v) * 16
-      line_pass(b1 + off, b0 + off, h, row_bytes);
+    for (int tsk = threadIdx.x; tsk < w * VEC * col_chunks; tsk += kPoolThreads) {
+      const int line = tsk % (w * VEC), chunk = tsk / (w * VEC);
+      const uint32_t off = static_cast<uint32_t>(line) * 16u;   // (x * VEC + v) * 16
+      chunk_pass(b1 + off, b0 + off, h, row_bytes, chunk * CH);
     }
     fence_proxy_async_smem();
     __syncthreads();
