@@ -31,7 +31,7 @@ def main():
     torch.cuda.synchronize()
     L, st = eng.L, torch.cuda.current_stream().cuda_stream
     cap = 1 << 21
-    buf = torch.zeros(2 + 8 * cap, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(2 + 12 * cap, dtype=torch.int64, device="cuda")
     import pynvml as nv
     nv.nvmlInit()
     h = nv.nvmlDeviceGetHandleByIndex(0)
@@ -62,7 +62,7 @@ def main():
         th.join()
         check(L.tod_debug_set_timeline(None), "timeline off")
         cnt = min(int(buf[0]), cap)
-        rec = buf[2:2 + 8 * cnt].view(-1, 8).cpu().numpy()
+        rec = buf[2:2 + 12 * cnt].view(-1, 12).cpu().numpy()
         sm = (rec[:, 1] & 0xffff).astype(np.int64)
         cyc = (rec[:, 1].astype(np.uint64) >> np.uint64(16)).astype(np.int64)
         t1 = rec[:, 3].astype(np.int64)

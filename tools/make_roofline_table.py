@@ -45,9 +45,10 @@ print(f"\nConv launches: {tot_ms * 1e3:.0f} µs measured against {tot_bound * 1e
 if tl:
     print("\n## Inside the captured graph (tools/timeline.py: one record per CTA, two plans alternating)\n")
     print("`pdl` = CTA start -> programmatic-launch wait returned; `fill` = -> first accumulator complete; `steady` = first -> last accumulator; "
-          "`drain` = last accumulator -> CTA exit; GHz = SM cycle counter / globaltimer over the CTA.\n")
-    print("| launch | kernel | CTAs/launch | span µs (first CTA start -> last CTA end) | µs per CTA | pdl | fill | steady | drain | GHz |")
-    print("|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+          "`drain` = last accumulator -> CTA exit; `wOp` / `wAcc` = share of the MMA role's lifetime spent waiting for operands (A / B landed) / for a "
+          "free accumulator (the epilogue); GHz = SM cycle counter / globaltimer over the CTA.\n")
+    print("| launch | kernel | CTAs/launch | span µs (first CTA start -> last CTA end) | µs per CTA | pdl | fill | steady | drain | wOp % | wAcc % | GHz |")
+    print("|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     reps = tl["args"]["replays"] // tl["args"]["plans"]
     seen = set()
     for r in tl["launches"]:
@@ -58,6 +59,6 @@ if tl:
             continue
         seen.add(key)
         print(f"| {r['id']} | {r['name']} | {r['ctas'] // max(reps, 1)} | {r.get('span_us', 0):.1f} | {r['cta_us_mean']:.1f} | {r['wait_us']:.1f} | {r['fill_us']:.1f} | "
-              f"{r.get('steady_us', 0):.1f} | {r.get('drain_us', 0):.1f} | {r.get('ghz', 0):.2f} |")
+              f"{r.get('steady_us', 0):.1f} | {r.get('drain_us', 0):.1f} | {r.get('mma_wait_operands_pct', 0):.0f} | {r.get('mma_wait_acc_pct', 0):.0f} | {r.get('ghz', 0):.2f} |")
         if r["name"].startswith("nms segments"):
             break

@@ -34,7 +34,7 @@ def main():
     engs = [model.engine(a.batch, a.size, a.size, dev, instance=i) for i in range(a.plans)]
     L = engs[0].L
     cap = 1 << 20
-    buf = torch.zeros(2 + 8 * cap, dtype=torch.int64, device=dev)
+    buf = torch.zeros(2 + 12 * cap, dtype=torch.int64, device=dev)
     buf[1] = cap
     check(L.tod_debug_set_timeline(buf.data_ptr()), "set timeline")
     graphs = [e.graph_for("u8", 0, 0.05, 0.5) for e in engs]            # captured WITH the tags (the warm-up pass records too)
@@ -66,7 +66,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     n = int(buf[0])
-    rec = buf[2:2 + 8 * min(n, cap)].view(-1, 8).cpu().numpy()
+    rec = buf[2:2 + 12 * min(n, cap)].view(-1, 12).cpu().numpy()
     check(L.tod_debug_set_timeline(None), "clear timeline")
     ids, sm, t0, t1 = (rec[:, 0] & 0xffffffff).astype(np.int64), (rec[:, 1] & 0xffff).astype(np.int64), rec[:, 2].astype(np.int64), rec[:, 3].astype(np.int64)
     cyc_end = (rec[:, 1].astype(np.uint64) >> np.uint64(16)).astype(np.int64)          # SM cycle counter (48 bits) at CTA end
@@ -128,20 +128,24 @@ def main():
         cuts = np.nonzero(np.diff(ts0) > 400000)[0] + 1          # a new replay starts > 0.4 ms after the previous CTA start
         spans = [float(ts1[a_:b_].max() - ts0[a_:b_].min()) / 1e3 for a_, b_ in zip(np.r_[0, cuts], np.r_[cuts, len(ts0)]) if b_ > a_]
         span_us = float(np.median(spans)) if spans else 0.0
+        mc, wo, wa = rec[sel, 8].astype(np.float64), rec[sel, 9].astype(np.float64), rec[sel, 10].astype(np.float64)
+        has = mc > 0
+        wait_op_pct = float(100 * wo[has].sum() / mc[has].sum()) if has.any() else 0.0
+        wait_acc_pct = float(100 * wa[has].sum() / mc[has].sum()) if has.any() else 0.0
         mma_end, last = t_mma[sel], t_last[sel]
         steady_us = float(np.where((last > 0) & (acc > 0), last - acc, 0).mean() / 1e3)      # first -> last accumulator complete
         drain_us = float(np.where(last > 0, t1[sel] - last, 0).mean() / 1e3)                # last accumulator -> CTA end
         mma_tail_us = float(np.where(mma_end > 0, t1[sel] - mma_end, 0).mean() / 1e3)       # MMA role done -> CTA end
-        rows.append({"steady_us": steady_us, "drain_us": drain_us, "mma_tail_us": mma_tail_us, "span_us": span_us,
+        rows.append({"mma_wait_operands_pct": wait_op_pct, "mma_wait_acc_pct": wait_acc_pct, "steady_us": steady_us, "drain_us": drain_us, "mma_tail_us": mma_tail_us, "span_us": span_us,
                      "ghz": (ghz_num[int(i)] / ghz_den[int(i)]) if ghz_den.get(int(i)) else 0.0,
                      "id": int(i), "name": names[i] if i < len(names) else "?", "ctas": int(sel.sum()),
                      "cta_us_mean": float(dur.mean() / 1e3), "cta_us_max": float(dur.max() / 1e3), "wait_us": wait_us, "fill_us": fill_us,
                      "sm_time_share": float(dur.sum() / total_cta_ns), "sm_us_per_step": float(dur.sum() / 1e3 / n_sm / a.replays * 1.0)})
     # one graph = one set of ids per plan; fold the plans' copies of the same layer together by name order
-    print(f"{'launch':>6s} {'kernel':40s} {'CTAs':>7s} {'span us':>8s} {'us/CTA':>8s} {'max':>8s} {'pdl-wait':>9s} {'fill':>6s} {'steady':>7s} {'drain':>6s} {'GHz':>5s} {'SM-us/step':>11s} {'share':>7s}")
+    print(f"{'launch':>6s} {'kernel':40s} {'CTAs':>7s} {'span us':>8s} {'us/CTA':>8s} {'max':>8s} {'pdl-wait':>9s} {'fill':>6s} {'steady':>7s} {'drain':>6s} {'wOp%':>5s} {'wAcc%':>5s} {'GHz':>5s} {'SM-us/step':>11s} {'share':>7s}")
     for r in rows:
         print(f"{r['id']:6d} {r['name']:40s} {r['ctas']:7d} {r['span_us']:8.1f} {r['cta_us_mean']:8.1f} {r['cta_us_max']:8.1f} {r['wait_us']:9.1f} {r['fill_us']:6.1f} "
-              f"{r['steady_us']:7.1f} {r['drain_us']:6.1f} {r['ghz']:5.2f} {r['sm_us_per_step']:11.1f} {100 * r['sm_time_share']:6.2f}%")
+              f"{r['steady_us']:7.1f} {r['drain_us']:6.1f} {r['mma_wait_operands_pct']:5.1f} {r['mma_wait_acc_pct']:5.1f} {r['ghz']:5.2f} {r['sm_us_per_step']:11.1f} {100 * r['sm_time_share']:6.2f}%")
     by_name = {}
     for r in rows:
         by_name.setdefault(r["name"], 0.0)

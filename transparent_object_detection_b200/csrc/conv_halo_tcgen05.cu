@@ -326,13 +326,14 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
   uint64_t* const p_full_bar = &tail_bars[TAIL ? 1 : 0];
   uint64_t* const d2_full_bar = &tail_bars[TAIL ? 3 : 0];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ unsigned long long tl_marks[4];   // timeline: programmatic wait returned / first accumulator complete / MMA role done / last accumulator complete
+  __shared__ unsigned long long tl_marks[7];   // timeline: programmatic wait returned / first accumulator complete / MMA role done / last accumulator complete
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const unsigned long long tl_t0 = (p.tl.buf != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
-  if (p.tl.buf != nullptr && threadIdx.x == 0) tl_marks[0] = tl_marks[1] = tl_marks[2] = tl_marks[3] = 0;
+  if (p.tl.buf != nullptr && threadIdx.x == 0)
+    for (int i = 0; i < 7; ++i) tl_marks[i] = 0;
 
   // persistent schedule: this CTA owns N tile `nt`.  Full rounds are interleaved (CTA g takes super-tile r * G + g, so
   // the grid streams through adjacent memory together); what is left after the last full round is split evenly at
@@ -533,7 +534,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     const bool mma_thread = elect_one();
     if (mma_thread) prefetch_weights();   // (both CTAs of a pair: each its own halves)
     if ((!PAIR || rank == 0) && mma_thread) {
-    WaitClock wc(p.prof != nullptr);
+    WaitClock wc(p.prof != nullptr || p.tl.buf != nullptr);
     const long long role_t0 = wc.begin();
     // The whole role is instantiated per K-step count (4 / 2 / generic) and the sub-tile loop is unrolled (m <= 4): at
     // N <= 64 one MMA is <= 48 tensor cycles and the ~25 uniform-datapath instructions (constant reloads, three K-step
@@ -661,7 +662,13 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     if (p.tl.buf != nullptr) tl_marks[2] = global_timer_ns();
     if (wc.on) {
       wc.end(0, role_t0);
-      for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
+      if (p.prof != nullptr)
+        for (int i = 0; i < 4; ++i) p.prof[blockIdx.x * 16 + 3 + i] = wc.acc[i];
+      if (p.tl.buf != nullptr) {
+        tl_marks[4] = wc.acc[0];   // role lifetime
+        tl_marks[5] = wc.acc[3];   // waiting for operands (A / B full)
+        tl_marks[6] = wc.acc[1];   // waiting for a free accumulator
+      }
     }
     }   // elected lane
     __syncwarp();
@@ -1123,7 +1130,7 @@ conv_halo_tcgen05(const __grid_constant__ HaloParams p) {
     if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
-  if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1], tl_marks[2], tl_marks[3]);
+  if (threadIdx.x == 0) timeline_write(p.tl, tl_t0, tl_marks[0], tl_marks[1], tl_marks[2], tl_marks[3], tl_marks[4], tl_marks[5], tl_marks[6]);
 }
 
 // ------------------------------------------------------------------------------------------------ host

@@ -49,7 +49,7 @@ __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * 
 // tod_debug_set_timeline(d_buf): every instrumented kernel launched afterwards appends one record per CTA --
 // {launch id | blockIdx << 32, smid, globaltimer at CTA start, at CTA end, after the programmatic-launch wait, at the
 // first complete accumulator} -- to d_buf (header: cursor,
-// capacity; then 8 x u64 records).  The tag is baked into a launch at enqueue / capture time, so a CUDA graph captured
+// capacity; then 12 x u64 records).  The tag is baked into a launch at enqueue / capture time, so a CUDA graph captured
 // while the timeline is set keeps recording on every replay: that is how tools/timeline.py sees which kernels overlap
 // INSIDE the captured graph (ncu serialises kernels, and nsys is not in this image).  Null tag = no code executed.
 struct TimelineTag {
@@ -68,15 +68,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 // t_ready: the programmatic-launch wait returned (0 if the kernel has none); t_acc: the first accumulator was complete;
 // t_mma_end: the MMA role issued its last commit; t_last_acc: the last accumulator was complete (what follows is drain)
+// mma_cycles / wait_operand_cycles / wait_acc_cycles: the MMA role's lifetime and the cycles it spent waiting for operands
+// (A / B full barriers) and for a free accumulator, so that stalls can be attributed INSIDE the captured graph
 __device__ __forceinline__ void timeline_write(const TimelineTag& tag, unsigned long long t0, unsigned long long t_ready = 0,
                                                unsigned long long t_acc = 0, unsigned long long t_mma_end = 0,
-                                               unsigned long long t_last_acc = 0) {
+                                               unsigned long long t_last_acc = 0, unsigned long long mma_cycles = 0,
+                                               unsigned long long wait_operand_cycles = 0, unsigned long long wait_acc_cycles = 0) {
   if (tag.buf == nullptr) return;
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   const unsigned long long slot = atomicAdd(tag.buf, 1ull);
   if (slot < tag.buf[1]) {
-    unsigned long long* r = tag.buf + 2 + 8 * slot;
+    unsigned long long* r = tag.buf + 2 + 12 * slot;
     r[0] = static_cast<unsigned long long>(static_cast<unsigned>(tag.id)) | (static_cast<unsigned long long>(blockIdx.x) << 32);
     r[1] = smid | (static_cast<unsigned long long>(clock64()) << 16);   // low 48 bits of the SM cycle counter at CTA end
     r[2] = t0;
@@ -85,6 +88,10 @@ __device__ __forceinline__ void timeline_write(const TimelineTag& tag, unsigned 
     r[5] = t_acc;
     r[6] = t_mma_end;
     r[7] = t_last_acc;
+    r[8] = mma_cycles;
+    r[9] = wait_operand_cycles;
+    r[10] = wait_acc_cycles;
+    r[11] = 0;
   }
 }
 
